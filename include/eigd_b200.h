@@ -1,0 +1,127 @@
+/*
+ * eigd_b200 -- C-ABI of the B200-native gradient path of smdogroup/eigd.
+ *
+ * The reference is pure Python (no FFI of its own); the drop-in boundary is the public
+ * surface of `eigd/eigenvector_derivatives.py` + `eigd/arpack.py`.  This header declares
+ * the entry points that sit directly beneath that surface.  Each group cites the reference
+ * code whose arithmetic it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; `eigd_last_error()` gives
+ *     a message for the last failure on the calling thread;
+ *   - pointers named d_* are DEVICE pointers (fp64 / int32 unless said otherwise), all
+ *     others are host pointers; no ownership ever passes across the boundary except for
+ *     the opaque handles created/destroyed here;
+ *   - dense multi-vectors are addressed as X[i*rs + c*cs] (row stride, column stride in
+ *     elements), which covers both the reference's (n, N) row-major arrays
+ *     (rs = N, cs = 1; eigd/eigenvector_derivatives.py:56-65) and Krylov bases stored one
+ *     vector per row (rs = 1, cs = n);
+ *   - all kernels are launched on the stream set with eigd_set_stream (default: stream 0).
+ */
+#ifndef EIGD_B200_H
+#define EIGD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- library / context --------------------------------------------------------------- */
+int eigd_version(void);
+const char* eigd_last_error(void);
+int eigd_device_count(int* count);
+int eigd_set_stream(void* cuda_stream);
+/* number of kernels this library has launched since load (bench.py "gpu_launches") */
+int64_t eigd_launch_count(void);
+
+/* ---- sparse products: replaces scipy `B @ x`, `A @ x` (csr_matvec[s]) used at
+ *      eigd/eigenvector_derivatives.py:255-265,519,609,800-857,975-1010,1173-1252,1500 --- */
+/* Y = alpha * A @ X + beta * Y,  A CSR (n rows), X and Y with (rs, cs) strides, k columns */
+int eigd_csr_spmm(int n, const int* d_indptr, const int* d_indices, const double* d_vals,
+                  const double* d_X, int64_t xrs, int64_t xcs,
+                  double* d_Y, int64_t yrs, int64_t ycs, int k, double alpha, double beta);
+/* out = a*va + b*vb on the value arrays of two matrices sharing one pattern
+ * (K - sigma*M at examples/natural_frequency.py:338, Kr + sigma*Gr at examples/buckling.py:582) */
+int eigd_axpby(int64_t len, double a, const double* d_x, double b, const double* d_y, double* d_out);
+
+/* ---- tall-skinny dense kernels: replaces numpy `V.T @ X`, `U @ t`, `.dot`, axpy loops
+ *      (eigd/eigenvector_derivatives.py:26-30,502,519,616-620,1254-1260,1529-1538,1648,1979) */
+/* C[a*ldc + b] = sum_i X[i*xrs + a*xcs] * Y[i*yrs + b*ycs]; k1,k2 <= 64; workspace >= eigd_gemm_tn_workspace() doubles */
+int64_t eigd_gemm_tn_workspace(int k1, int k2);
+int eigd_gemm_tn(int64_t n, int k1, int k2, const double* d_X, int64_t xrs, int64_t xcs,
+                 const double* d_Y, int64_t yrs, int64_t ycs, double* d_C, int ldc, double* d_work);
+/* Y[i,b] = beta*Y[i,b] + alpha * sum_a X[i,a] * S[a*lds + b]; S on device; k1 <= 128, k2 <= 64 */
+int eigd_gemm_nn(int64_t n, int k1, int k2, double alpha, const double* d_X, int64_t xrs, int64_t xcs,
+                 const double* d_S, int lds, double beta, double* d_Y, int64_t yrs, int64_t ycs);
+/* out[c] = sum_i X[i,c]*Y[i,c] (column-wise dots, k <= 64) */
+int eigd_col_dot(int64_t n, int k, const double* d_X, int64_t xrs, int64_t xcs,
+                 const double* d_Y, int64_t yrs, int64_t ycs, double* d_out, double* d_work);
+/* Y[i,c] += sign * s[c] * X[i,c]   (s on device) */
+int eigd_col_axpy(int64_t n, int k, double sign, const double* d_s, const double* d_X, int64_t xrs, int64_t xcs,
+                  double* d_Y, int64_t yrs, int64_t ycs);
+/* X[i,c] *= s[c]  (mode 0)   or   X[i,c] /= s[c]  (mode 1)   or X[i,c] /= sqrt(s[c]) (mode 2) */
+int eigd_col_scale(int64_t n, int k, int mode, const double* d_s, double* d_X, int64_t xrs, int64_t xcs);
+/* Y[i,c] = X[i,c] (strided copy / transpose) */
+int eigd_copy2d(int64_t n, int k, const double* d_X, int64_t xrs, int64_t xcs, double* d_Y, int64_t yrs, int64_t ycs);
+
+/* ---- sparse LDL^T of the shifted matrix: replaces scipy.sparse.linalg.splu + SuperLU.solve
+ *      behind SpLuOperator (eigd/eigenvector_derivatives.py:11-23) ------------------------ */
+typedef struct eigd_symbolic eigd_symbolic;
+typedef struct eigd_factor eigd_factor;
+
+/* Symbolic analysis of a structurally symmetric CSR pattern (host arrays).
+ * coords: optional (n_nodes x dim) node coordinates for geometric nested dissection, with
+ * dof_per_node consecutive rows per node (NULL -> graph-based dissection).
+ * opts: optional int[8] {leaf_cols, max_super_cols, nd_leaf, relax, 0...}; NULL -> defaults. */
+int eigd_symbolic_create(int n, const int* indptr, const int* indices,
+                         const double* coords, int dim, int dof_per_node,
+                         const int* opts, eigd_symbolic** out);
+void eigd_symbolic_destroy(eigd_symbolic* s);
+/* scalar queries: what = 0 n, 1 nsuper, 2 nlevels, 3 nnz(L) (strict lower, dense fronts),
+ * 4 front storage doubles, 5 sum of front sizes, 6 max front size, 7 max supernode cols,
+ * 8 flops of the factorisation, 9 nnz of exact (unrelaxed) L */
+int64_t eigd_symbolic_query(const eigd_symbolic* s, int what);
+/* array getters (host copies): which = 0 perm[n] (new->old), 1 etree parent[n], 2 sn_first[nsuper+1],
+ * 3 sn_rowptr[nsuper+1], 4 sn_rows[...], 5 sn_parent[nsuper], 6 sn_level[nsuper],
+ * 7 front_off[nsuper+1], 8 rel[...] (aligned with sn_rows), 9 colcount[n], 10 level_ptr[nlevels+1],
+ * 11 level_sn[nsuper].  Returns the element count; copies min(count, cap) int64 values. */
+int64_t eigd_symbolic_get(const eigd_symbolic* s, int which, int64_t* out, int64_t cap);
+/* assembly map nz -> slot in front storage (or -1), computed by host code */
+int eigd_symbolic_assembly_map_host(const eigd_symbolic* s, int n, const int* indptr, const int* indices, int64_t* out_map);
+/* the same map computed by the CUDA integer kernel (device CSR in, device map out) */
+int eigd_symbolic_assembly_map_device(eigd_symbolic* s, int n, const int* d_indptr, const int* d_indices, int64_t* d_map);
+
+int eigd_factor_create(eigd_symbolic* s, int max_rhs, eigd_factor** out);
+void eigd_factor_destroy(eigd_factor* f);
+/* numeric factorisation from device CSR values + device assembly map */
+int eigd_factor_numeric(eigd_factor* f, int64_t nnz, const double* d_vals, const int64_t* d_map);
+/* info[0] = #negative pivots (inertia), info[1] = #perturbed pivots, info[2] = #non-finite */
+int eigd_factor_info(eigd_factor* f, int64_t* info3);
+/* X = (L D L^T)^{-1} B in the original ordering; k columns, (rs, cs) strides; X may alias B */
+int eigd_factor_solve(eigd_factor* f, const double* d_B, int64_t brs, int64_t bcs,
+                      double* d_X, int64_t xrs, int64_t xcs, int k);
+int64_t eigd_factor_bytes(const eigd_factor* f);
+
+/* ---- element kernels: replaces the numpy einsum callbacks and assembly in
+ *      examples/thermal.py:126-246, examples/natural_frequency.py:134-284 ------------------ */
+/* kind: 0 = thermal Q4 (1 dof/node), 1 = plane-stress Q4 (2 dof/node).
+ * Element matrices Ke (stiffness-like) and Me (mass-like) are scattered through
+ * d_emap[e*ne*ne + a*ne + b] (position in the CSR value array), ne = 4*dof.
+ * ks[e], ms[e]: per-element material scale factors already penalised. */
+int eigd_q4_assemble(int kind, int nelems, const int* d_conn, const double* d_xy,
+                     const double* d_ks, const double* d_ms, const double* cmat6,
+                     const int64_t* d_emap, int64_t nnz, double* d_Kvals, double* d_Mvals);
+/* out_e[e] = sA * sum_k wA_e^T (dKe/ds) v_e  -  sB * sum_k wB_e^T (dMe/dm) v_e  per element
+ * (unit-scale element matrices; caller multiplies the penalisation derivative in d_dk, d_dm).
+ * WA, WB, V are (ndof, N) row-major with leading dimension ldw. */
+int eigd_q4_quadforms(int kind, int nelems, const int* d_conn, const double* d_xy, const double* cmat6,
+                      const double* d_WA, const double* d_WB, const double* d_V, int N, int ldw,
+                      const double* d_dk, const double* d_dm, double sA, double sB, double* d_out);
+/* node_out[v] = scale * sum_{e in adj(v)} e_vals[e]   (gather form of np.add.at, thermal.py:612-615) */
+int eigd_node_gather(int nnodes, const int* d_nptr, const int* d_nelem, const double* d_evals, double scale, double* d_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
