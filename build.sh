@@ -1,0 +1,19 @@
+#!/bin/bash
+# Builds eigd_b200/libeigd_b200.so for sm_100a (cross-compiles without a GPU).
+set -e
+cd "$(dirname "$0")"
+SRC=eigd_b200/csrc
+OUT=eigd_b200/libeigd_b200.so
+mkdir -p build
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -O3 ${EIGD_NVCC_EXTRA}"
+pids=()
+for f in dense sparse factor fe; do
+  $NVCC $FLAGS -c $SRC/$f.cu -o build/$f.o &
+  pids+=($!)
+done
+g++ -O3 -std=c++17 -fPIC -c $SRC/symbolic.cpp -o build/symbolic.o &
+pids+=($!)
+for p in "${pids[@]}"; do wait $p; done
+$NVCC -shared -o $OUT build/dense.o build/sparse.o build/factor.o build/fe.o build/symbolic.o -lcudart
+echo "built $OUT"

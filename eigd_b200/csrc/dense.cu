@@ -1,0 +1,328 @@
+// Tall-skinny fp64 kernels (all HBM-bound): X^T Y, X S, column-wise dots / axpys / scalings.
+// They replace the numpy expressions `V.T @ X`, `U @ t`, `x.dot(y)`, `X -= h * W` in
+// reference eigd/eigenvector_derivatives.py:26-30 (_project), :502-519 (laa), :616-620 (dl),
+// :1228-1260 (sibk Gram-Schmidt), :1529-1538 (Lanczos Gram-Schmidt), :1648 (Rayleigh-Ritz).
+//
+// Operands are addressed as X[i*rs + c*cs]: (rs=k, cs=1) is the reference's (n, N) row-major
+// layout, (rs=1, cs=n) is a Krylov basis stored one vector per row.  Tiles are staged through
+// shared memory with the unit-stride index varying fastest across the warp, so global loads
+// are coalesced for either layout.  Reductions over n are two-stage and deterministic.
+#include "common.cuh"
+#include "../../include/eigd_b200.h"
+
+cudaStream_t g_eigd_stream = 0;
+int64_t g_eigd_launches = 0;
+
+extern "C" int eigd_set_stream(void* s) { g_eigd_stream = (cudaStream_t)s; return 0; }
+extern "C" int64_t eigd_launch_count(void) { return g_eigd_launches; }
+extern "C" int eigd_device_count(int* count) {
+  int c = 0;
+  cudaError_t e = cudaGetDeviceCount(&c);
+  if (e != cudaSuccess) { *count = 0; eigd_set_error("cudaGetDeviceCount: %s", cudaGetErrorString(e)); cudaGetLastError(); return 100 + (int)e; }
+  *count = c;
+  return 0;
+}
+
+namespace {
+
+constexpr int TN_R = 64;        // rows per tile
+constexpr int TN_KMAX = 32;     // max columns of either operand per launch
+constexpr int TN_THREADS = 256;
+constexpr int RED_MAX_CTAS = 296;
+
+// stage a (rows x k) tile of a strided operand into shared memory, tile[r*(k+1) + c]
+__device__ __forceinline__ void load_tile(double* tile, const double* __restrict__ X, int64_t rs, int64_t cs,
+                                          int64_t row0, int rows, int k, int ldt) {
+  int total = rows * k;
+  if (cs == 1) {
+    for (int e = threadIdx.x; e < total; e += blockDim.x) {
+      int r = e / k, c = e - r * k;
+      tile[r * ldt + c] = X[(row0 + r) * rs + c];
+    }
+  } else {
+    for (int e = threadIdx.x; e < total; e += blockDim.x) {
+      int c = e / rows, r = e - c * rows;
+      tile[r * ldt + c] = X[(row0 + r) * rs + (int64_t)c * cs];
+    }
+  }
+}
+
+// partial[cta][a*k2+b] = sum over the CTA's row tiles of X[i,a]*Y[i,b]; 4x4 register tiles
+__global__ void __launch_bounds__(TN_THREADS)
+gemm_tn_partial(int64_t n, int k1, int k2, const double* __restrict__ X, int64_t xrs, int64_t xcs,
+                const double* __restrict__ Y, int64_t yrs, int64_t ycs, double* __restrict__ partial) {
+  extern __shared__ double sm[];
+  const int ldx = k1 + 1, ldy = k2 + 1;
+  double* Xs = sm;
+  double* Ys = sm + TN_R * ldx;
+  const int nta = (k1 + 3) >> 2, ntb = (k2 + 3) >> 2;
+  const int npairs = nta * ntb;
+  const int G = TN_THREADS / npairs;  // row groups (npairs <= 64 -> G >= 4)
+  const int g = threadIdx.x / npairs, p = threadIdx.x - g * npairs;
+  const int a0 = (p / ntb) * 4, b0 = (p % ntb) * 4;
+  const bool active = g < G;
+  double acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+  const int64_t ntiles = (n + TN_R - 1) / TN_R;
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    int64_t row0 = t * TN_R;
+    int rows = (int)min((int64_t)TN_R, n - row0);
+    load_tile(Xs, X, xrs, xcs, row0, rows, k1, ldx);
+    load_tile(Ys, Y, yrs, ycs, row0, rows, k2, ldy);
+    __syncthreads();
+    if (active) {
+      for (int r = g; r < rows; r += G) {
+        double xa[4], yb[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) xa[i] = (a0 + i < k1) ? Xs[r * ldx + a0 + i] : 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) yb[j] = (b0 + j < k2) ? Ys[r * ldy + b0 + j] : 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fma(xa[i], yb[j], acc[i][j]);
+      }
+    }
+    __syncthreads();
+  }
+  // reduce over the row groups in a fixed order: group 0 owns the result
+  double* red = sm;  // reuse: needs 16 * TN_THREADS doubles = 32 KB <= tile storage? sized by host
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) red[(i * 4 + j) * TN_THREADS + threadIdx.x] = active ? acc[i][j] : 0.0;
+  __syncthreads();
+  if (g == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (a0 + i < k1 && b0 + j < k2) {
+          double s = 0.0;
+          for (int gg = 0; gg < G; ++gg) s += red[(i * 4 + j) * TN_THREADS + gg * npairs + p];
+          partial[(int64_t)blockIdx.x * (k1 * k2) + (a0 + i) * k2 + (b0 + j)] = s;
+        }
+      }
+  }
+}
+
+// C[a*ldc + b] = sum_cta partial[cta][a*k2+b]
+__global__ void reduce_partials(int ncta, int k1, int k2, const double* __restrict__ partial, double* __restrict__ C, int ldc) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= k1 * k2) return;
+  double s = 0.0;
+  for (int c = 0; c < ncta; ++c) s += partial[(int64_t)c * (k1 * k2) + e];
+  C[(e / k2) * ldc + (e % k2)] = s;
+}
+
+constexpr int NN_R = 32;
+constexpr int NN_K1MAX = 64;
+constexpr int NN_K2MAX = 32;
+
+// Y[i,b] = beta*Y[i,b] + alpha*sum_a X[i,a]*S[a,b]
+__global__ void __launch_bounds__(256)
+gemm_nn_kernel(int64_t n, int k1, int k2, double alpha, const double* __restrict__ X, int64_t xrs, int64_t xcs,
+               const double* __restrict__ S, int lds, double beta, double* __restrict__ Y, int64_t yrs, int64_t ycs) {
+  __shared__ double Ss[NN_K1MAX * NN_K2MAX];
+  __shared__ double Xs[NN_R * (NN_K1MAX + 1)];
+  const int ldx = k1 + 1;
+  for (int e = threadIdx.x; e < k1 * k2; e += blockDim.x) Ss[e] = S[(e / k2) * lds + (e % k2)];
+  const int64_t ntiles = (n + NN_R - 1) / NN_R;
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    int64_t row0 = t * NN_R;
+    int rows = (int)min((int64_t)NN_R, n - row0);
+    __syncthreads();
+    load_tile(Xs, X, xrs, xcs, row0, rows, k1, ldx);
+    __syncthreads();
+    int total = rows * k2;
+    for (int e = threadIdx.x; e < total; e += blockDim.x) {
+      int r, b;
+      if (ycs == 1) { r = e / k2; b = e - r * k2; } else { b = e / rows; r = e - b * rows; }
+      double s = 0.0;
+      for (int a = 0; a < k1; ++a) s = fma(Xs[r * ldx + a], Ss[a * k2 + b], s);
+      int64_t yi = (row0 + r) * yrs + (int64_t)b * ycs;
+      double y0 = (beta == 0.0) ? 0.0 : beta * Y[yi];
+      Y[yi] = fma(alpha, s, y0);
+    }
+  }
+}
+
+// partial[cta][c] = sum_i X[i,c]*Y[i,c] over the CTA's rows
+__global__ void __launch_bounds__(256)
+col_dot_partial(int64_t n, int k, const double* __restrict__ X, int64_t xrs, int64_t xcs,
+                const double* __restrict__ Y, int64_t yrs, int64_t ycs, double* __restrict__ partial) {
+  __shared__ double red[256];
+  const int RG = 256 / k;  // row lanes per column
+  const int rr = threadIdx.x / k, c = threadIdx.x - rr * k;
+  // when both operands are unit-stride along rows (k == 1 style) the mapping below is still coalesced
+  double acc = 0.0;
+  if (rr < RG) {
+    for (int64_t i = (int64_t)blockIdx.x * RG + rr; i < n; i += (int64_t)gridDim.x * RG)
+      acc = fma(X[i * xrs + (int64_t)c * xcs], Y[i * yrs + (int64_t)c * ycs], acc);
+  }
+  red[threadIdx.x] = (rr < RG) ? acc : 0.0;
+  __syncthreads();
+  if (rr == 0) {
+    double s = 0.0;
+    for (int g = 0; g < RG; ++g) s += red[g * k + c];
+    partial[(int64_t)blockIdx.x * k + c] = s;
+  }
+}
+
+__global__ void col_axpy_kernel(int64_t n, int k, double sign, const double* __restrict__ s, const double* __restrict__ X,
+                                int64_t xrs, int64_t xcs, double* __restrict__ Y, int64_t yrs, int64_t ycs) {
+  int64_t total = n * k;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    int64_t i; int c;
+    if (ycs == 1) { i = e / k; c = (int)(e - i * k); } else { c = (int)(e / n); i = e - (int64_t)c * n; }
+    int64_t yi = i * yrs + (int64_t)c * ycs;
+    Y[yi] = fma(sign * s[c], X[i * xrs + (int64_t)c * xcs], Y[yi]);
+  }
+}
+
+__global__ void col_scale_kernel(int64_t n, int k, int mode, const double* __restrict__ s, double* __restrict__ X,
+                                 int64_t xrs, int64_t xcs) {
+  int64_t total = n * k;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    int64_t i; int c;
+    if (xcs == 1) { i = e / k; c = (int)(e - i * k); } else { c = (int)(e / n); i = e - (int64_t)c * n; }
+    double f = s[c];
+    if (mode == 1) f = 1.0 / f;
+    else if (mode == 2) f = 1.0 / sqrt(f);
+    X[i * xrs + (int64_t)c * xcs] *= f;
+  }
+}
+
+// tiled transpose-capable copy: coalesced on both sides
+__global__ void copy2d_kernel(int64_t n, int k, const double* __restrict__ X, int64_t xrs, int64_t xcs,
+                              double* __restrict__ Y, int64_t yrs, int64_t ycs) {
+  __shared__ double tile[32][33];
+  int64_t i0 = (int64_t)blockIdx.x * 32;
+  int c0 = blockIdx.y * 32;
+  // read with the source's unit-stride index fastest
+  for (int q = threadIdx.y; q < 32; q += blockDim.y) {
+    int64_t i; int c;
+    if (xcs == 1) { i = i0 + q; c = c0 + threadIdx.x; } else { i = i0 + threadIdx.x; c = c0 + q; }
+    if (i < n && c < k) tile[(int)(i - i0)][c - c0] = X[i * xrs + (int64_t)c * xcs];
+  }
+  __syncthreads();
+  for (int q = threadIdx.y; q < 32; q += blockDim.y) {
+    int64_t i; int c;
+    if (ycs == 1) { i = i0 + q; c = c0 + threadIdx.x; } else { i = i0 + threadIdx.x; c = c0 + q; }
+    if (i < n && c < k) Y[i * yrs + (int64_t)c * ycs] = tile[(int)(i - i0)][c - c0];
+  }
+}
+
+__global__ void axpby_kernel(int64_t len, double a, const double* __restrict__ x, double b, const double* __restrict__ y,
+                             double* __restrict__ out) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < len; e += (int64_t)gridDim.x * blockDim.x)
+    out[e] = a * x[e] + (b == 0.0 ? 0.0 : b * y[e]);
+}
+
+inline int tn_grid(int64_t n) {
+  int64_t t = (n + TN_R - 1) / TN_R;
+  return (int)(t < RED_MAX_CTAS ? (t < 1 ? 1 : t) : RED_MAX_CTAS);
+}
+
+}  // namespace
+
+extern "C" int64_t eigd_gemm_tn_workspace(int k1, int k2) {
+  (void)k1; (void)k2;
+  return (int64_t)RED_MAX_CTAS * TN_KMAX * TN_KMAX;
+}
+
+extern "C" int eigd_gemm_tn(int64_t n, int k1, int k2, const double* X, int64_t xrs, int64_t xcs, const double* Y,
+                            int64_t yrs, int64_t ycs, double* C, int ldc, double* work) {
+  if (n <= 0 || k1 <= 0 || k2 <= 0) return 0;
+  for (int a0 = 0; a0 < k1; a0 += TN_KMAX) {
+    int ka = min(TN_KMAX, k1 - a0);
+    for (int b0 = 0; b0 < k2; b0 += TN_KMAX) {
+      int kb = min(TN_KMAX, k2 - b0);
+      int grid = tn_grid(n);
+      size_t tile_bytes = (size_t)TN_R * (ka + 1 + kb + 1) * sizeof(double);
+      size_t red_bytes = (size_t)16 * TN_THREADS * sizeof(double);
+      size_t smem = tile_bytes > red_bytes ? tile_bytes : red_bytes;
+      EIGD_LAUNCH(gemm_tn_partial, grid, TN_THREADS, smem, n, ka, kb, X + (int64_t)a0 * xcs, xrs, xcs,
+                  Y + (int64_t)b0 * ycs, yrs, ycs, work);
+      EIGD_CHECK_LAUNCH();
+      EIGD_LAUNCH(reduce_partials, (ka * kb + 255) / 256, 256, 0, grid, ka, kb, work, C + (int64_t)a0 * ldc + b0, ldc);
+      EIGD_CHECK_LAUNCH();
+    }
+  }
+  return 0;
+}
+
+extern "C" int eigd_gemm_nn(int64_t n, int k1, int k2, double alpha, const double* X, int64_t xrs, int64_t xcs,
+                            const double* S, int lds, double beta, double* Y, int64_t yrs, int64_t ycs) {
+  if (n <= 0 || k2 <= 0) return 0;
+  int64_t tiles = (n + NN_R - 1) / NN_R;
+  int grid = (int)(tiles < 148 * 8 ? tiles : 148 * 8);
+  if (k1 <= 0) {  // Y = beta*Y
+    return 0;
+  }
+  for (int b0 = 0; b0 < k2; b0 += NN_K2MAX) {
+    int kb = min(NN_K2MAX, k2 - b0);
+    for (int a0 = 0; a0 < k1; a0 += NN_K1MAX) {
+      int ka = min(NN_K1MAX, k1 - a0);
+      EIGD_LAUNCH(gemm_nn_kernel, grid, 256, 0, n, ka, kb, alpha, X + (int64_t)a0 * xcs, xrs, xcs,
+                  S + (int64_t)a0 * lds + b0, lds, (a0 == 0 ? beta : 1.0), Y + (int64_t)b0 * ycs, yrs, ycs);
+      EIGD_CHECK_LAUNCH();
+    }
+  }
+  return 0;
+}
+
+extern "C" int eigd_col_dot(int64_t n, int k, const double* X, int64_t xrs, int64_t xcs, const double* Y, int64_t yrs,
+                            int64_t ycs, double* out, double* work) {
+  if (k <= 0) return 0;
+  for (int c0 = 0; c0 < k; c0 += 64) {
+    int kc = min(64, k - c0);
+    int RG = 256 / kc;
+    int64_t want = (n + (int64_t)RG * 8 - 1) / ((int64_t)RG * 8);
+    int grid = (int)(want < 1 ? 1 : (want > RED_MAX_CTAS ? RED_MAX_CTAS : want));
+    EIGD_LAUNCH(col_dot_partial, grid, 256, 0, n, kc, X + (int64_t)c0 * xcs, xrs, xcs, Y + (int64_t)c0 * ycs, yrs, ycs, work);
+    EIGD_CHECK_LAUNCH();
+    EIGD_LAUNCH(reduce_partials, 1, 64, 0, grid, 1, kc, work, out + c0, kc);
+    EIGD_CHECK_LAUNCH();
+  }
+  return 0;
+}
+
+static inline int ew_grid(int64_t total) {
+  int64_t g = (total + 255) / 256;
+  return (int)(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g));
+}
+
+extern "C" int eigd_col_axpy(int64_t n, int k, double sign, const double* s, const double* X, int64_t xrs, int64_t xcs,
+                             double* Y, int64_t yrs, int64_t ycs) {
+  if (n <= 0 || k <= 0) return 0;
+  EIGD_LAUNCH(col_axpy_kernel, ew_grid(n * k), 256, 0, n, k, sign, s, X, xrs, xcs, Y, yrs, ycs);
+  EIGD_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int eigd_col_scale(int64_t n, int k, int mode, const double* s, double* X, int64_t xrs, int64_t xcs) {
+  if (n <= 0 || k <= 0) return 0;
+  EIGD_LAUNCH(col_scale_kernel, ew_grid(n * k), 256, 0, n, k, mode, s, X, xrs, xcs);
+  EIGD_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int eigd_copy2d(int64_t n, int k, const double* X, int64_t xrs, int64_t xcs, double* Y, int64_t yrs, int64_t ycs) {
+  if (n <= 0 || k <= 0) return 0;
+  dim3 grid((unsigned)((n + 31) / 32), (unsigned)((k + 31) / 32));
+  dim3 block(32, 8);
+  EIGD_LAUNCH(copy2d_kernel, grid, block, 0, n, k, X, xrs, xcs, Y, yrs, ycs);
+  EIGD_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int eigd_axpby(int64_t len, double a, const double* x, double b, const double* y, double* out) {
+  if (len <= 0) return 0;
+  EIGD_LAUNCH(axpby_kernel, ew_grid(len), 256, 0, len, a, x, b, y, out);
+  EIGD_CHECK_LAUNCH();
+  return 0;
+}

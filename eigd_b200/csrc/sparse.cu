@@ -1,0 +1,91 @@
+// CSR sparse products Y = alpha*A@X + beta*Y for one or many right-hand sides.
+// Replaces scipy's csr_matvec / csr_matvecs behind `B @ x`, `A @ x` in the reference
+// (eigd/eigenvector_derivatives.py:255-265, 519, 609, 800-857, 975-1010, 1173-1252, 1500).
+//
+// k == 1 : a group of G lanes walks one row's non-zeros (coalesced index/value loads),
+//          shuffle reduction inside the group.
+// k  > 1 : a group of G >= k lanes owns one row; lane c accumulates column c, so each
+//          matrix entry is loaded once (broadcast) and the k-wide slice of X is one
+//          contiguous, coalesced read in the reference's (n, N) row-major layout.
+// Algorithmic bytes: nnz*12 + (n+1)*4 + 2*n*k*8.
+#include "common.cuh"
+#include "../../include/eigd_b200.h"
+
+namespace {
+
+template <int G>
+__global__ void __launch_bounds__(256)
+spmv_kernel(int n, const int* __restrict__ indptr, const int* __restrict__ indices, const double* __restrict__ vals,
+            const double* __restrict__ X, int64_t xrs, double* __restrict__ Y, int64_t yrs, double alpha, double beta) {
+  const int lane = threadIdx.x & (G - 1);
+  const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+  const int64_t ngroups = ((int64_t)gridDim.x * blockDim.x) / G;
+  // the loop bound is uniform across the warp (first group of the warp), so the shuffles
+  // below always run with all 32 lanes converged
+  const int gw = (threadIdx.x & 31) / G;  // group index inside the warp
+  for (int64_t row = gid; row - gw < n; row += ngroups) {
+    const bool valid = row < n;
+    int p0 = 0, p1 = 0;
+    if (valid) { p0 = indptr[row]; p1 = indptr[row + 1]; }
+    double acc = 0.0;
+    for (int p = p0 + lane; p < p1; p += G) acc = fma(vals[p], X[(int64_t)indices[p] * xrs], acc);
+#pragma unroll
+    for (int o = G >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o, G);
+    if (valid && lane == 0) {
+      double y0 = (beta == 0.0) ? 0.0 : beta * Y[row * yrs];
+      Y[row * yrs] = fma(alpha, acc, y0);
+    }
+  }
+}
+
+template <int G>
+__global__ void __launch_bounds__(256)
+spmm_kernel(int n, const int* __restrict__ indptr, const int* __restrict__ indices, const double* __restrict__ vals,
+            const double* __restrict__ X, int64_t xrs, int64_t xcs, double* __restrict__ Y, int64_t yrs, int64_t ycs,
+            int k, double alpha, double beta) {
+  const int lane = threadIdx.x & (G - 1);
+  const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+  const int64_t ngroups = ((int64_t)gridDim.x * blockDim.x) / G;
+  for (int64_t row = gid; row < n; row += ngroups) {
+    int p0 = indptr[row], p1 = indptr[row + 1];
+    double acc = 0.0;
+    if (lane < k) {
+      for (int p = p0; p < p1; ++p)
+        acc = fma(vals[p], X[(int64_t)indices[p] * xrs + (int64_t)lane * xcs], acc);
+      int64_t yi = row * yrs + (int64_t)lane * ycs;
+      double y0 = (beta == 0.0) ? 0.0 : beta * Y[yi];
+      Y[yi] = fma(alpha, acc, y0);
+    }
+  }
+}
+
+inline int grid_for(int64_t groups_needed, int groups_per_block) {
+  int64_t g = (groups_needed + groups_per_block - 1) / groups_per_block;
+  int64_t cap = 148 * 32;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+
+extern "C" int eigd_csr_spmm(int n, const int* indptr, const int* indices, const double* vals, const double* X,
+                             int64_t xrs, int64_t xcs, double* Y, int64_t yrs, int64_t ycs, int k, double alpha,
+                             double beta) {
+  if (n <= 0 || k <= 0) return 0;
+  if (k == 1) {
+    EIGD_LAUNCH(spmv_kernel<8>, grid_for(n, 256 / 8), 256, 0, n, indptr, indices, vals, X, xrs, Y, yrs, alpha, beta);
+    EIGD_CHECK_LAUNCH();
+    return 0;
+  }
+  for (int c0 = 0; c0 < k; c0 += 32) {
+    int kc = k - c0 < 32 ? k - c0 : 32;
+    const double* Xc = X + (int64_t)c0 * xcs;
+    double* Yc = Y + (int64_t)c0 * ycs;
+    if (kc <= 2) EIGD_LAUNCH(spmm_kernel<2>, grid_for(n, 128), 256, 0, n, indptr, indices, vals, Xc, xrs, xcs, Yc, yrs, ycs, kc, alpha, beta);
+    else if (kc <= 4) EIGD_LAUNCH(spmm_kernel<4>, grid_for(n, 64), 256, 0, n, indptr, indices, vals, Xc, xrs, xcs, Yc, yrs, ycs, kc, alpha, beta);
+    else if (kc <= 8) EIGD_LAUNCH(spmm_kernel<8>, grid_for(n, 32), 256, 0, n, indptr, indices, vals, Xc, xrs, xcs, Yc, yrs, ycs, kc, alpha, beta);
+    else if (kc <= 16) EIGD_LAUNCH(spmm_kernel<16>, grid_for(n, 16), 256, 0, n, indptr, indices, vals, Xc, xrs, xcs, Yc, yrs, ycs, kc, alpha, beta);
+    else EIGD_LAUNCH(spmm_kernel<32>, grid_for(n, 8), 256, 0, n, indptr, indices, vals, Xc, xrs, xcs, Yc, yrs, ycs, kc, alpha, beta);
+    EIGD_CHECK_LAUNCH();
+  }
+  return 0;
+}

@@ -1,0 +1,385 @@
+"""Thin device layer: torch owns HBM buffers and streams, every arithmetic op is one of the
+hand-written kernels in libeigd_b200.so reached through the C-ABI (include/eigd_b200.h).
+
+All dense operands are 2-D torch CUDA fp64 tensors of *logical* shape (n, k); their strides
+are passed through unchanged, so a Krylov basis stored one vector per row is simply used as
+``Vt.T``.  Nothing here falls back to the CPU: without the library or without a CUDA device
+every call raises.
+"""
+import ctypes
+import hashlib
+
+import numpy as np
+
+from . import _lib
+from ._lib import check
+
+try:
+    import torch
+except Exception as exc:  # pragma: no cover
+    raise ImportError("eigd_b200 needs torch for device buffers") from exc
+
+
+F64 = torch.float64
+
+
+class _State:
+    device = None
+    work = None
+    ready = False
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def init(device=None):
+    """Select the CUDA device and allocate the reduction workspace."""
+    lib = _lib.load()
+    if not torch.cuda.is_available():
+        raise _lib.EigdNativeError("eigd_b200: no CUDA device visible (there is no CPU fallback)")
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    device = torch.device(device)
+    if _State.ready and _State.device == device:
+        return device
+    torch.cuda.set_device(device)
+    _State.device = device
+    nwork = lib.eigd_gemm_tn_workspace(32, 32)
+    _State.work = torch.empty(int(nwork), dtype=F64, device=device)
+    # run on torch's current stream so torch.cuda.Event timing and torch ops order with us
+    check(lib.eigd_set_stream(ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)), "set_stream")
+    _State.ready = True
+    return device
+
+
+def dev():
+    if not _State.ready:
+        init()
+    return _State.device
+
+
+def launch_count():
+    return int(_lib.load().eigd_launch_count())
+
+
+def to_device(x, dtype=F64):
+    """numpy / torch -> CUDA tensor (no copy if already there)."""
+    d = dev()
+    if isinstance(x, torch.Tensor):
+        return x.to(device=d, dtype=dtype)
+    return torch.as_tensor(np.ascontiguousarray(x), device=d).to(dtype)
+
+
+def empty(*shape):
+    return torch.empty(*shape, dtype=F64, device=dev())
+
+
+def zeros(*shape):
+    return torch.zeros(*shape, dtype=F64, device=dev())
+
+
+def _as2d(x):
+    if x.dim() == 1:
+        return x.unsqueeze(1)
+    if x.dim() != 2:
+        raise ValueError("expected a 1-D or 2-D tensor")
+    return x
+
+
+def _chk(x, name="operand"):
+    if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == F64):
+        raise TypeError("%s must be a CUDA float64 tensor" % name)
+    return x
+
+
+# ------------------------------------------------------------------------------------------
+# sparse matrices
+# ------------------------------------------------------------------------------------------
+class CsrDevice:
+    """CSR matrix resident in HBM (int32 structure, fp64 values)."""
+
+    def __init__(self, indptr, indices, data, shape):
+        d = dev()
+        self.shape = tuple(int(s) for s in shape)
+        self.indptr = torch.as_tensor(np.ascontiguousarray(indptr, dtype=np.int32), device=d) \
+            if not isinstance(indptr, torch.Tensor) else indptr.to(device=d, dtype=torch.int32)
+        self.indices = torch.as_tensor(np.ascontiguousarray(indices, dtype=np.int32), device=d) \
+            if not isinstance(indices, torch.Tensor) else indices.to(device=d, dtype=torch.int32)
+        self.data = to_device(data)
+        self.nnz = int(self.indices.numel())
+        self.dtype = np.dtype(np.float64)
+
+    @classmethod
+    def from_scipy(cls, A):
+        import scipy.sparse as sp
+        A = sp.csr_matrix(A)
+        if not A.has_sorted_indices:
+            A = A.sorted_indices()
+        return cls(A.indptr, A.indices, A.data, A.shape)
+
+    def with_values(self, data):
+        out = object.__new__(CsrDevice)
+        out.shape, out.indptr, out.indices, out.nnz, out.dtype = self.shape, self.indptr, self.indices, self.nnz, self.dtype
+        out.data = _chk(data, "values")
+        return out
+
+    def spmm(self, X, out=None, alpha=1.0, beta=0.0):
+        """out = alpha * A @ X + beta * out"""
+        X2 = _as2d(_chk(X, "X"))
+        n, k = self.shape[0], X2.shape[1]
+        if X2.shape[0] != self.shape[1]:
+            raise ValueError("dimension mismatch in spmm")
+        if out is None:
+            out = empty(n, k) if X.dim() == 2 else empty(n)
+            beta = 0.0
+        Y2 = _as2d(_chk(out, "out"))
+        check(_lib.load().eigd_csr_spmm(n, _ptr(self.indptr), _ptr(self.indices), _ptr(self.data),
+                                        _ptr(X2), X2.stride(0), X2.stride(1), _ptr(Y2), Y2.stride(0), Y2.stride(1),
+                                        k, float(alpha), float(beta)), "csr_spmm")
+        return out
+
+    def __matmul__(self, X):
+        return self.spmm(X)
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+        return sp.csr_matrix((self.data.cpu().numpy(), self.indices.cpu().numpy(), self.indptr.cpu().numpy()), shape=self.shape)
+
+
+def axpby(a, x, b, y, out=None):
+    """out = a*x + b*y on flat value arrays (shifted-matrix values)."""
+    if out is None:
+        out = torch.empty_like(x)
+    check(_lib.load().eigd_axpby(x.numel(), float(a), _ptr(x), float(b), _ptr(y) if y is not None else None, _ptr(out)), "axpby")
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# tall-skinny dense ops
+# ------------------------------------------------------------------------------------------
+def gemm_tn(X, Y, out=None):
+    """C = X^T Y  (k1 x k2)"""
+    X2, Y2 = _as2d(_chk(X)), _as2d(_chk(Y))
+    n, k1, k2 = X2.shape[0], X2.shape[1], Y2.shape[1]
+    if Y2.shape[0] != n:
+        raise ValueError("dimension mismatch in gemm_tn")
+    if out is None:
+        out = empty(k1, k2)
+    check(_lib.load().eigd_gemm_tn(n, k1, k2, _ptr(X2), X2.stride(0), X2.stride(1), _ptr(Y2), Y2.stride(0), Y2.stride(1),
+                                   _ptr(out), out.stride(0), _ptr(_State.work)), "gemm_tn")
+    return out
+
+
+def gemm_nn(X, S, Y, alpha=1.0, beta=0.0):
+    """Y = beta*Y + alpha * X @ S, S a small (k1 x k2) device matrix"""
+    X2, Y2 = _as2d(_chk(X)), _as2d(_chk(Y))
+    S2 = _as2d(_chk(S))
+    n, k1, k2 = X2.shape[0], X2.shape[1], Y2.shape[1]
+    if S2.shape != (k1, k2) or Y2.shape[0] != n:
+        raise ValueError("dimension mismatch in gemm_nn: X %s S %s Y %s" % (tuple(X2.shape), tuple(S2.shape), tuple(Y2.shape)))
+    if S2.stride(1) != 1 and S2.shape[1] != 1:
+        S2 = S2.contiguous()
+    lds = S2.stride(0) if S2.shape[0] > 1 else max(k2, 1)
+    check(_lib.load().eigd_gemm_nn(n, k1, k2, float(alpha), _ptr(X2), X2.stride(0), X2.stride(1), _ptr(S2), lds,
+                                   float(beta), _ptr(Y2), Y2.stride(0), Y2.stride(1)), "gemm_nn")
+    return Y
+
+
+def col_dot(X, Y, out=None):
+    X2, Y2 = _as2d(_chk(X)), _as2d(_chk(Y))
+    n, k = X2.shape
+    if out is None:
+        out = empty(k)
+    check(_lib.load().eigd_col_dot(n, k, _ptr(X2), X2.stride(0), X2.stride(1), _ptr(Y2), Y2.stride(0), Y2.stride(1),
+                                   _ptr(out), _ptr(_State.work)), "col_dot")
+    return out
+
+
+def col_axpy(Y, s, X, sign=1.0):
+    """Y[:, c] += sign * s[c] * X[:, c]"""
+    X2, Y2 = _as2d(_chk(X)), _as2d(_chk(Y))
+    n, k = Y2.shape
+    check(_lib.load().eigd_col_axpy(n, k, float(sign), _ptr(_chk(s, "s")), _ptr(X2), X2.stride(0), X2.stride(1),
+                                    _ptr(Y2), Y2.stride(0), Y2.stride(1)), "col_axpy")
+    return Y
+
+
+def col_scale(X, s, mode=0):
+    """mode 0: X *= s ; 1: X /= s ; 2: X /= sqrt(s)   (per column, s on device)"""
+    X2 = _as2d(_chk(X))
+    n, k = X2.shape
+    check(_lib.load().eigd_col_scale(n, k, int(mode), _ptr(_chk(s, "s")), _ptr(X2), X2.stride(0), X2.stride(1)), "col_scale")
+    return X
+
+
+def copy2d(src, dst):
+    S2, D2 = _as2d(_chk(src)), _as2d(_chk(dst))
+    if S2.shape != D2.shape:
+        raise ValueError("shape mismatch in copy2d")
+    n, k = S2.shape
+    check(_lib.load().eigd_copy2d(n, k, _ptr(S2), S2.stride(0), S2.stride(1), _ptr(D2), D2.stride(0), D2.stride(1)), "copy2d")
+    return dst
+
+
+def project(U, V, X):
+    """Oblique projection X <- X - U (V^T X)   (reference _project, eigenvector_derivatives.py:26-30)"""
+    t = gemm_tn(V, X)
+    gemm_nn(U, t, X, alpha=-1.0, beta=1.0)
+    return X
+
+
+# ------------------------------------------------------------------------------------------
+# symbolic analysis + numeric factorisation
+# ------------------------------------------------------------------------------------------
+_SYM_NAMES = ["perm", "parent", "sn_first", "sn_rowptr", "sn_rows", "sn_parent", "sn_level",
+              "front_off", "rel", "colcount", "level_ptr", "level_sn"]
+_QUERY = {"n": 0, "nsuper": 1, "nlevels": 2, "nnzL": 3, "front_doubles": 4, "sum_front": 5,
+          "max_front": 6, "max_cols": 7, "flops": 8, "exact_nnzL": 9}
+
+
+class Symbolic:
+    """Host-side symbolic analysis of a symmetric CSR pattern (works without a GPU)."""
+
+    def __init__(self, indptr, indices, n, coords=None, dof_per_node=1, opts=None):
+        lib = _lib.load()
+        self.n = int(n)
+        self._indptr = np.ascontiguousarray(indptr, dtype=np.int32)
+        self._indices = np.ascontiguousarray(indices, dtype=np.int32)
+        h = ctypes.c_void_p()
+        cptr, dim = None, 0
+        if coords is not None:
+            coords = np.ascontiguousarray(coords, dtype=np.float64)
+            dim = coords.shape[1]
+            cptr = coords.ctypes.data_as(ctypes.c_void_p)
+        optr = None
+        if opts is not None:
+            o = list(opts) + [0] * (8 - len(opts))
+            oarr = (ctypes.c_int * 8)(*o)
+            optr = ctypes.cast(oarr, ctypes.c_void_p)
+        check(lib.eigd_symbolic_create(self.n, self._indptr.ctypes.data_as(ctypes.c_void_p),
+                                       self._indices.ctypes.data_as(ctypes.c_void_p), cptr, dim, int(dof_per_node),
+                                       optr, ctypes.byref(h)), "symbolic_create")
+        self.handle = h
+        self._dmap_cache = {}
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                _lib.load().eigd_symbolic_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def query(self, name):
+        return int(_lib.load().eigd_symbolic_query(self.handle, _QUERY[name]))
+
+    def stats(self):
+        return {k: self.query(k) for k in _QUERY}
+
+    def get(self, name):
+        lib = _lib.load()
+        which = _SYM_NAMES.index(name)
+        cnt = lib.eigd_symbolic_get(self.handle, which, None, 0)
+        out = np.zeros(cnt, dtype=np.int64)
+        lib.eigd_symbolic_get(self.handle, which, out.ctypes.data_as(ctypes.c_void_p), cnt)
+        return out
+
+    def arrays(self):
+        return {nm: self.get(nm) for nm in _SYM_NAMES}
+
+    def assembly_map_host(self, indptr=None, indices=None):
+        ip = self._indptr if indptr is None else np.ascontiguousarray(indptr, dtype=np.int32)
+        ix = self._indices if indices is None else np.ascontiguousarray(indices, dtype=np.int32)
+        out = np.zeros(len(ix), dtype=np.int64)
+        check(_lib.load().eigd_symbolic_assembly_map_host(self.handle, self.n, ip.ctypes.data_as(ctypes.c_void_p),
+                                                          ix.ctypes.data_as(ctypes.c_void_p),
+                                                          out.ctypes.data_as(ctypes.c_void_p)), "assembly_map_host")
+        return out
+
+    def assembly_map_device(self, d_indptr, d_indices):
+        """CSR nz -> front slot, computed by the CUDA integer kernel."""
+        out = torch.empty(d_indices.numel(), dtype=torch.int64, device=dev())
+        check(_lib.load().eigd_symbolic_assembly_map_device(self.handle, self.n, _ptr(d_indptr), _ptr(d_indices), _ptr(out)),
+              "assembly_map_device")
+        return out
+
+
+def pattern_key(indptr, indices, extra=b""):
+    h = hashlib.blake2b(digest_size=16)
+    h.update(np.ascontiguousarray(indptr).view(np.uint8))
+    h.update(np.ascontiguousarray(indices).view(np.uint8))
+    h.update(extra)
+    return h.hexdigest()
+
+
+class Factor:
+    """Numeric LDL^T on the device for a fixed symbolic analysis."""
+
+    def __init__(self, symbolic, max_rhs=32):
+        dev()
+        self.sym = symbolic
+        self.n = symbolic.n
+        h = ctypes.c_void_p()
+        check(_lib.load().eigd_factor_create(symbolic.handle, int(max_rhs), ctypes.byref(h)), "factor_create")
+        self.handle = h
+        self.max_rhs = int(max_rhs)
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                _lib.load().eigd_factor_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def numeric(self, d_vals, d_map):
+        check(_lib.load().eigd_factor_numeric(self.handle, d_vals.numel(), _ptr(_chk(d_vals)), _ptr(d_map)), "factor_numeric")
+        return self
+
+    def info(self):
+        out = (ctypes.c_int64 * 3)()
+        check(_lib.load().eigd_factor_info(self.handle, ctypes.cast(out, ctypes.c_void_p)), "factor_info")
+        return {"negative_pivots": int(out[0]), "perturbed_pivots": int(out[1]), "non_finite": int(out[2])}
+
+    def nbytes(self):
+        return int(_lib.load().eigd_factor_bytes(self.handle))
+
+    def solve(self, B, out=None):
+        """out = (L D L^T)^{-1} B for a (n,) or (n, k) device tensor; out may alias B."""
+        B2 = _as2d(_chk(B, "B"))
+        if B2.shape[0] != self.n:
+            raise ValueError("dimension mismatch in solve")
+        if out is None:
+            out = torch.empty_like(B)
+        X2 = _as2d(_chk(out, "out"))
+        check(_lib.load().eigd_factor_solve(self.handle, _ptr(B2), B2.stride(0), B2.stride(1), _ptr(X2), X2.stride(0),
+                                            X2.stride(1), B2.shape[1]), "factor_solve")
+        return out
+
+
+# ------------------------------------------------------------------------------------------
+# element kernels
+# ------------------------------------------------------------------------------------------
+def q4_quadforms(kind, conn, xy, cmat6, WA, WB, V, dk, dm, sA, sB, out):
+    nelems = conn.shape[0]
+    N = V.shape[1]
+    ldw = V.stride(0)
+    for t in (WA, WB):
+        if t is not None and (t.stride(0) != ldw or t.stride(1) != 1):
+            raise ValueError("WA/WB/V must share one row-major layout")
+    if V.stride(1) != 1:
+        raise ValueError("V must be row-major")
+    check(_lib.load().eigd_q4_quadforms(int(kind), nelems, _ptr(conn), _ptr(xy), _ptr(cmat6), _ptr(WA), _ptr(WB), _ptr(V),
+                                        N, ldw, _ptr(dk), _ptr(dm), float(sA), float(sB), _ptr(out)), "q4_quadforms")
+    return out
+
+
+def q4_assemble(kind, conn, xy, ks, ms, cmat6, src_ptr, src, nnz, Kvals, Mvals):
+    check(_lib.load().eigd_q4_assemble(int(kind), conn.shape[0], _ptr(conn), _ptr(xy), _ptr(ks), _ptr(ms), _ptr(cmat6),
+                                       _ptr(src_ptr), _ptr(src), int(nnz), _ptr(Kvals), _ptr(Mvals)), "q4_assemble")
+
+
+def node_gather(nptr, nelem, evals, scale, out):
+    check(_lib.load().eigd_node_gather(out.numel(), _ptr(nptr), _ptr(nelem), _ptr(evals), float(scale), _ptr(out)), "node_gather")
+    return out

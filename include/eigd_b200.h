@@ -105,17 +105,20 @@ int64_t eigd_factor_bytes(const eigd_factor* f);
 
 /* ---- element kernels: replaces the numpy einsum callbacks and assembly in
  *      examples/thermal.py:126-246, examples/natural_frequency.py:134-284 ------------------ */
-/* kind: 0 = thermal Q4 (1 dof/node), 1 = plane-stress Q4 (2 dof/node).
- * Element matrices Ke (stiffness-like) and Me (mass-like) are scattered through
- * d_emap[e*ne*ne + a*ne + b] (position in the CSR value array), ne = 4*dof.
- * ks[e], ms[e]: per-element material scale factors already penalised. */
+/* kind: 0 = thermal Q4 (1 dof/node), 1 = plane-stress Q4 (2 dof/node), ne = 4*dof.
+ * Gather-form assembly (deterministic, no atomics): CSR non-zero p receives the sum of its
+ * sources d_src[d_src_ptr[p] .. d_src_ptr[p+1]), each encoded as e*ne*ne + a*ne + b (the
+ * flattened `Ke.flatten()` order of examples/thermal.py:79-92, natural_frequency.py:90-104).
+ * ks[e], ms[e]: per-element penalised material factors. cmat6 = C0 {c00,c01,c02,c11,c12,c22}
+ * (device, may be NULL for kind 0).  d_Kvals / d_Mvals may be NULL. */
 int eigd_q4_assemble(int kind, int nelems, const int* d_conn, const double* d_xy,
-                     const double* d_ks, const double* d_ms, const double* cmat6,
-                     const int64_t* d_emap, int64_t nnz, double* d_Kvals, double* d_Mvals);
-/* out_e[e] = sA * sum_k wA_e^T (dKe/ds) v_e  -  sB * sum_k wB_e^T (dMe/dm) v_e  per element
- * (unit-scale element matrices; caller multiplies the penalisation derivative in d_dk, d_dm).
- * WA, WB, V are (ndof, N) row-major with leading dimension ldw. */
-int eigd_q4_quadforms(int kind, int nelems, const int* d_conn, const double* d_xy, const double* cmat6,
+                     const double* d_ks, const double* d_ms, const double* d_cmat6,
+                     const int64_t* d_src_ptr, const int64_t* d_src, int64_t nnz,
+                     double* d_Kvals, double* d_Mvals);
+/* out[e] += sA * dk[e] * sum_k wA_e^T Ke1 v_e  -  sB * dm[e] * sum_k wB_e^T Me1 v_e  per element,
+ * Ke1 / Me1 the unit-material element matrices, dk / dm the penalisation derivatives (NULL -> 1).
+ * WA, WB, V are (ndof, N) row-major with leading dimension ldw; WA or WB may be NULL. */
+int eigd_q4_quadforms(int kind, int nelems, const int* d_conn, const double* d_xy, const double* d_cmat6,
                       const double* d_WA, const double* d_WB, const double* d_V, int N, int ldw,
                       const double* d_dk, const double* d_dm, double sA, double sB, double* d_out);
 /* node_out[v] = scale * sum_{e in adj(v)} e_vals[e]   (gather form of np.add.at, thermal.py:612-615) */

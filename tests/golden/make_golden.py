@@ -1,0 +1,146 @@
+"""Regenerates the golden fixtures in this directory from the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference):
+    python tests/golden/make_golden.py
+The reference is loaded through oracle/ref_loader.py (scipy>=1.15 compatibility shim that
+leaves eigd/eigenvector_derivatives.py untouched).  Each fixture freezes the inputs (CSR A, B,
+shift, adjoint right-hand sides) and the reference's outputs (eigenpairs, adjoints, gradients)
+of one small seeded case.  Krylov bases of the ARPACK path are not reproducible (random start
+vector), so for IRAM only converged quantities are stored; the seeded BasicLanczos path also
+stores its basis and tridiagonal coefficients.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", "..", "oracle"))
+import ref_loader as rl  # noqa: E402
+
+SIBK = {"lanczos_guess": True, "update_guess": False, "bs_target": 1}
+
+
+def csr_dict(prefix, A):
+    A = A.tocsr()
+    A.sort_indices()
+    return {prefix + "_indptr": A.indptr.astype(np.int32), prefix + "_indices": A.indices.astype(np.int32),
+            prefix + "_data": A.data.copy(), prefix + "_shape": np.array(A.shape)}
+
+
+def corr_to_array(data):
+    rows = [(i, j, xi, eta) for i, items in sorted(data.items()) for (j, xi, eta) in items]
+    return np.array(rows, dtype=float).reshape(-1, 4)
+
+
+def thermal_case(solver_type, methods, nx=24, ny=20, N=6, m=30, seed=3):
+    th = rl.load_example("thermal")
+    out = {}
+    for method in methods:
+        opts = dict(SIBK) if method == "sibk" else ({} if method == "laa" else {"lanczos_guess": method != "dl"})
+        np.random.seed(seed)
+        topo = th.make_model(nx=nx, ny=ny, Lx=1.0, Ly=0.8, N=N, m=m, solver_type=solver_type, adjoint_method=method,
+                             adjoint_options=opts, rtol=1e-12, tol=1e-14 if solver_type != "IRAM" else 0.0)
+        topo.x[:] = np.random.uniform(0.3, 1.0, topo.x.shape)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            topo.initialize()
+            topo.initialize_adjoint()
+            vec = np.random.uniform(size=topo.nnodes)
+            topo.add_thermal_compliance_derivative(1.0, vec)
+            topo.finalize_adjoint()
+        if not out:
+            out.update(csr_dict("A", topo.K))
+            out.update(csr_dict("B", topo.M))
+            out.update(dict(sigma=topo.sigma, N=N, m=topo.eig_solver.m, x=topo.x.copy(), rhoE=topo.rhoE.copy(), vec=vec,
+                            conn=topo.conn, X=topo.X, r0=topo.fltr.r0, lam=topo.lam.copy(), Phi=topo.Q.copy(),
+                            Phib=topo.Qb.copy(), lamb=topo.lamb.copy(), nx=nx, ny=ny))
+            es = topo.eig_solver
+            if solver_type != "IRAM":
+                out.update(dict(m_max=es.m_max, alpha=es.alpha.copy(), beta=es.beta.copy(), V=es.V[:, :es.m].copy(), theta=es.theta.copy(),
+                                indices=es.indices.copy(), eig_res=es.eig_res.copy()))
+        out["psi_" + method] = topo.psi.copy()
+        out["corr_" + method] = corr_to_array(topo.profile["adjoint correction data"])
+        out["dfdx_" + method] = topo.rhoEb.copy()
+        out["xb_" + method] = topo.xb.copy()
+        res, orth = topo.eig_solver.eval_adjoint_residual_norm(topo.Qb, topo.psi, b_ortho=False)
+        out["res_" + method] = res
+        out["nsolves_" + method] = topo.profile["adjoint preconditioner count"]
+    return out
+
+
+def nf_case(nx=48, ny=24, N=6, seed=0):
+    nf = rl.load_example("natural_frequency")
+    np.random.seed(seed)
+    topo = nf.make_model(nx=nx, ny=ny, Lx=2.0, Ly=1.0, N=N, solver_type="IRAM", adjoint_method="sibk",
+                         adjoint_options=dict(SIBK), rtol=1e-12, deriv_type="tensor")
+    topo.x[:] = np.random.uniform(0.3, 1.0, topo.x.shape)
+    opt = nf.MinFreqOpt(topo, ks_param=1.0, fixed_mass=1.0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        topo.initialize()
+        topo.initialize_adjoint()
+        # seed of the adjoint: derivative of a smooth function of the flexible modes
+        w = np.random.uniform(size=topo.Q.shape)
+        topo.Qb[:] = w * 0.0
+        lam = topo.lam
+        for i in range(topo.N):
+            val = topo.Q[:, i] @ w[:, i]
+            topo.Qb[:, i] += 2.0 * val * w[:, i]
+            topo.lamb[i] += 0.3 * (i + 1)
+        topo.finalize_adjoint()
+    out = {}
+    out.update(csr_dict("A", topo.K))
+    out.update(csr_dict("B", topo.M))
+    es = topo.eig_solver
+    out.update(dict(sigma=topo.sigma, N=topo.N, Ncomp=len(es.lam), m=es.m, x=topo.x.copy(), rhoE=topo.rhoE.copy(),
+                    conn=topo.conn, X=topo.X, lam_all=es.lam.copy(), Phi_all=es.Phi.copy(), lam=topo.lam.copy(),
+                    Phi=topo.Q.copy(), Phib=topo.Qb.copy(), lamb=topo.lamb.copy(), psi=topo.psi.copy(),
+                    dfdx=topo.rhoEb.copy(), xb=topo.xb.copy(), nx=nx, ny=ny, w=w,
+                    corr=corr_to_array(topo.profile["adjoint correction data"])))
+    return out
+
+
+def buckling_case(solver_type="BasicLanczos", methods=("sibk", "pcpg"), nx=16, ny=32, N=5, seed=0):
+    bk = rl.load_example("buckling")
+    out = {}
+    for method in methods:
+        opts = dict(SIBK) if method == "sibk" else {"lanczos_guess": True}
+        np.random.seed(seed)
+        topo = bk.make_model(nx=nx, ny=ny, N=N, m=24, sigma=3.0, solver_type=solver_type, adjoint_method=method,
+                             adjoint_options=opts, rtol=1e-12, deriv_type="tensor")
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            topo.initialize()
+            topo.initialize_adjoint()
+            node = int(np.argmax(np.abs(topo.Q[:, 0])))
+            topo.add_eigenvector_aggregate_derivative(1.0, 100.0, node, mode="tanh")
+            topo.finalize_adjoint()
+        if not out:
+            out.update(csr_dict("A", topo.Gr))
+            out.update(csr_dict("B", topo.Kr))
+            es = topo.eig_solver
+            out.update(dict(sigma=topo.sigma, N=N, m=es.m, m_max=es.m_max, lam=topo.lam.copy(), Phi=topo.Qr.copy(), Phib=topo.Qrb.copy(),
+                            lamb=topo.lamb.copy(), reduced=np.array(topo.reduced), u=topo.u.copy(), rhoE=topo.rhoE.copy(),
+                            conn=topo.conn, X=topo.X, node=node, nx=nx, ny=ny))
+        out["psi_" + method] = topo.psir.copy()
+        out["corr_" + method] = corr_to_array(topo.profile["adjoint correction data"])
+        out["xb_" + method] = topo.xb.copy()
+    return out
+
+
+if __name__ == "__main__":
+    if not rl.reference_available():
+        raise SystemExit("reference tree not available; fixtures cannot be regenerated here")
+    cases = {
+        "thermal_basiclanczos": lambda: thermal_case("BasicLanczos", ["sibk", "laa", "dl", "pcpg", "pgmres"]),
+        "thermal_iram": lambda: thermal_case("IRAM", ["sibk"]),
+        "nf_iram": nf_case,
+        "buckling_basiclanczos": buckling_case,
+    }
+    for name, fn in cases.items():
+        d = fn()
+        path = os.path.join(HERE, name + ".npz")
+        np.savez_compressed(path, **d)
+        print(name, "->", path, "%.1f KB" % (os.path.getsize(path) / 1024))
