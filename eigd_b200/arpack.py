@@ -1,0 +1,226 @@
+"""Device-resident restarted shift-and-invert Lanczos behind the reference's ``eigsh_mod``.
+
+Mirrors the contract of reference ``eigd/arpack.py`` (``eigsh_mod`` at :104-118 returning
+``(d, z, Tm, v)`` as extracted at :58-101): ``d`` the k wanted eigenvalues in ascending order,
+``z`` their B-orthonormal eigenvectors (n, k), ``v`` the (n, ncv) B-orthonormal Krylov basis of
+the final factorisation and ``Tm = v^T B OP v`` its (ncv, ncv) projected operator.
+
+The reference drives ARPACK's implicitly restarted Lanczos (dsaupd/dseupd) on the host, one
+SuperLU solve and one SciPy SpMV per reverse-communication step.  Here the whole recurrence
+lives in HBM: the basis V and B*V are stored one vector per row, OP = (A - sigma B)^{-1} B is
+the multifrontal LDL^T solve plus a CSR SpMV, orthogonalisation is classical Gram-Schmidt with
+an unconditional second pass (DGKS) done as two tall-skinny GEMV pairs, and the only host work
+is the ncv x ncv symmetric eigenproblem once per restart cycle (one small D2H per cycle).
+Restarting is thick restart (Wu & Simon), which is mathematically equivalent to ARPACK's
+implicit restart with exact shifts; consequently ``Tm`` is diagonal-plus-arrow-plus-tridiagonal
+instead of tridiagonal, which the callers (``IRAM.solve``: ``eigh(T)``; ``laa``) do not care
+about.  Only the call pattern eigd uses is implemented (sigma given, OPinv given,
+which="LM", mode "normal" or "buckling"); the remaining scipy modes raise NotImplementedError
+because there is no CPU fallback to delegate to.
+"""
+import numpy as np
+import torch
+
+from . import device as D
+from ._hostdev import as_csr_device, to_dev, to_host, is_dev, small_to_dev
+
+
+class ArpackError(RuntimeError):
+    """Same role as scipy.sparse.linalg.ArpackError."""
+
+
+class ArpackNoConvergence(ArpackError):
+    def __init__(self, msg, eigenvalues, eigenvectors):
+        ArpackError.__init__(self, msg)
+        self.eigenvalues = eigenvalues
+        self.eigenvectors = eigenvectors
+
+
+class LanczosState:
+    """Device-side result of the restarted Lanczos process (kept by IRAM as its cache)."""
+
+    def __init__(self):
+        self.Vt = None       # (ncv, n) device, rows are B-orthonormal Krylov vectors
+        self.T = None        # (ncv, ncv) numpy
+        self.theta = None    # Ritz values of OP for the wanted set, in output order
+        self.d = None        # eigenvalues of the pencil (numpy, k)
+        self.Z = None        # (n, k) device eigenvectors
+        self.nops = 0        # operator applications (solves)
+        self.ncycles = 0
+        self.resid = None
+
+
+def _theta_to_lambda(theta, sigma, mode):
+    if mode == "normal":
+        return 1.0 / theta + sigma                      # eigd/eigenvector_derivatives.py:1960
+    return sigma * theta / (theta - 1.0)                # :1963
+
+
+def lanczos_thick_restart(Bip, factor, k, ncv, sigma, mode="normal", tol=0.0, maxiter=None, v0=None, seed=None):
+    """Thick-restart Lanczos on OP = factor o Bip in the Bip inner product; returns LanczosState."""
+    n = Bip.shape[0]
+    if ncv > n:
+        raise ValueError("ncv must be k<ncv<=n")
+    if maxiter is None:
+        maxiter = 10 * n
+    eps = np.finfo(np.float64).eps
+    if tol <= 0.0:
+        tol = eps
+    eps23 = eps ** (2.0 / 3.0)
+
+    Vt = D.empty(ncv + 1, n)
+    BVt = D.empty(ncv + 1, n)
+    tmp = D.empty(ncv, n)
+    hbuf = D.zeros(ncv + 1)
+    h2 = D.zeros(ncv + 1)
+    ab = D.zeros(2, ncv + 1)          # row 0: alpha_j, row 1: beta_j^2
+    st = LanczosState()
+
+    # start vector: forced into the range of OP as ARPACK's dgetv0 does
+    if v0 is not None:
+        w = to_dev(v0, copy=True).reshape(n)
+    else:
+        rng = np.random.default_rng(seed)
+        w = to_dev(rng.uniform(-1.0, 1.0, n))
+    bw = Bip.spmm(w)
+    v = factor.solve_dev(bw)
+    st.nops += 1
+    Bip.spmm(v, out=BVt[0])
+    nrm2 = D.col_dot(v, BVt[0])
+    Vt[0].copy_(v)
+    D.col_scale(Vt[0], nrm2, mode=2)
+    D.col_scale(BVt[0], nrm2, mode=2)
+
+    T = np.zeros((ncv, ncv))
+    j0 = 0
+    w = D.empty(n)
+    last_beta = 0.0
+    best = np.inf
+    stagnant = 0
+    while True:
+        for j in range(j0, ncv):
+            factor.solve_dev(BVt[j], out=w)
+            st.nops += 1
+            Vj, BVj = Vt[: j + 1].T, BVt[: j + 1].T          # logical (n, j+1), vector-major strides
+            h = hbuf[: j + 1]
+            g = h2[: j + 1]
+            D.gemm_tn(BVj, w, out=h.unsqueeze(1))
+            D.gemm_nn(Vj, h.unsqueeze(1), w, alpha=-1.0, beta=1.0)
+            D.gemm_tn(BVj, w, out=g.unsqueeze(1))            # second pass (DGKS)
+            D.gemm_nn(Vj, g.unsqueeze(1), w, alpha=-1.0, beta=1.0)
+            # alpha_j = h[j] + g[j]
+            D.axpby(1.0, h[j: j + 1], 1.0, g[j: j + 1], out=ab[0, j: j + 1])
+            Bip.spmm(w, out=BVt[j + 1])
+            D.col_dot(w, BVt[j + 1], out=ab[1, j: j + 1])
+            Vt[j + 1].copy_(w)
+            D.col_scale(Vt[j + 1], ab[1, j: j + 1], mode=2)
+            D.col_scale(BVt[j + 1], ab[1, j: j + 1], mode=2)
+        st.ncycles += 1
+        abh = to_host(ab)                                    # the one D2H of the cycle
+        if not np.all(np.isfinite(abh[:, j0:ncv])) or np.any(abh[1, j0:ncv] <= 0.0):
+            raise ArpackError("Lanczos breakdown: non-finite or non-positive B-norm (is B positive definite "
+                              "and the shifted matrix non-singular?)")
+        alpha = abh[0]
+        beta = np.sqrt(abh[1])
+        for j in range(j0, ncv):
+            T[j, j] = alpha[j]
+            if j + 1 < ncv:
+                T[j, j + 1] = T[j + 1, j] = beta[j]
+        last_beta = beta[ncv - 1]
+        theta, Y = np.linalg.eigh(T)
+        order = np.argsort(-np.abs(theta))                   # which = "LM"
+        bounds = np.abs(last_beta * Y[ncv - 1, :])
+        wanted = order[:k]
+        conv = bounds[wanted] <= tol * np.maximum(eps23, np.abs(theta[wanted]))
+        nconv = int(conv.sum())
+        worst = float(np.max(bounds[wanted] / np.maximum(eps23, np.abs(theta[wanted]))))
+        # the estimates bottom out near eps*|theta| (absolute accuracy of the small eigenvectors):
+        # accept when they stop improving at that level
+        if worst < 0.5 * best:
+            best, stagnant = worst, 0
+        else:
+            stagnant += 1
+        done = nconv == k or (worst <= 64.0 * eps and stagnant >= 1)
+        if done or st.nops >= maxiter or ncv >= n:
+            break
+        # ---- thick restart: keep the wanted Ritz vectors plus a share of the converged count --
+        kk = min(k + min(nconv, (ncv - k) // 2), ncv - 1)
+        if kk == 1 and ncv > 3:
+            kk = 2
+        keep = order[:kk]
+        Yk = small_to_dev(Y[:, keep])
+        D.gemm_nn(Vt[:ncv].T, Yk, tmp[:kk].T, alpha=1.0, beta=0.0)
+        Vt[:kk].copy_(tmp[:kk])
+        D.gemm_nn(BVt[:ncv].T, Yk, tmp[:kk].T, alpha=1.0, beta=0.0)
+        BVt[:kk].copy_(tmp[:kk])
+        Vt[kk].copy_(Vt[ncv])
+        BVt[kk].copy_(BVt[ncv])
+        T[:, :] = 0.0
+        T[np.arange(kk), np.arange(kk)] = theta[keep]
+        T[kk, :kk] = last_beta * Y[ncv - 1, keep]
+        T[:kk, kk] = T[kk, :kk]
+        j0 = kk
+
+    if nconv < k and not done:
+        lam = _theta_to_lambda(theta[wanted][conv], sigma, mode)
+        raise ArpackNoConvergence("ARPACK error -1: No convergence (%d iterations, %d/%d eigenvectors converged)"
+                                  % (st.nops, nconv, k), lam, None)
+    lam = _theta_to_lambda(theta[wanted], sigma, mode)
+    srt = np.argsort(lam)                                    # ascending algebraic order (eigd/arpack.py:237-239)
+    sel = wanted[srt]
+    st.d = lam[srt]
+    st.theta = theta[sel]
+    st.resid = bounds[sel]
+    st.T = T.copy()
+    st.Vt = Vt[:ncv]
+    Z = D.empty(n, k)
+    D.gemm_nn(st.Vt.T, small_to_dev(Y[:, sel]), Z, alpha=1.0, beta=0.0)
+    st.Z = Z
+    return st
+
+
+def eigsh_mod(A, k=6, M=None, sigma=None, which="LM", v0=None, ncv=None, maxiter=None, tol=0,
+              return_eigenvectors=True, Minv=None, OPinv=None, mode="normal", return_state=False, seed=None):
+    """Signature of reference eigd/arpack.py:104-118 (scipy's eigsh plus the 4-tuple return).
+
+    A : for mode="normal" unused beyond its shape; for mode="buckling" the matrix ARPACK
+        multiplies by (eigd passes the stiffness matrix, eigd/eigenvector_derivatives.py:1941-1942).
+    M : inner-product matrix of mode "normal".   OPinv : ``SpLuOperator`` of the shifted matrix.
+    Returns (d, z, Tm, v) as numpy arrays; with return_state=True the device-side LanczosState
+    is appended so callers can keep the basis in HBM.
+    """
+    n = A.shape[0]
+    if A.shape[0] != A.shape[1]:
+        raise ValueError(f"expected square matrix (shape={A.shape})")
+    if k <= 0:
+        raise ValueError("k must be greater than 0.")
+    if k >= n:
+        raise NotImplementedError("k >= n needs a dense eigensolver; not part of the device path")
+    if sigma is None or OPinv is None:
+        raise NotImplementedError("eigd_b200.eigsh_mod implements the call pattern eigd uses: sigma and OPinv given "
+                                  "(shift-invert); other scipy modes have no device implementation")
+    if which != "LM":
+        raise NotImplementedError("only which='LM' is implemented (the value eigd passes)")
+    if Minv is not None:
+        raise NotImplementedError("Minv is not used in shift-invert mode")
+    if mode == "normal":
+        if M is None:
+            raise NotImplementedError("standard (M=None) problems are outside eigd's call pattern")
+        Bip = as_csr_device(M)
+    elif mode == "buckling":
+        Bip = as_csr_device(A)
+    else:
+        raise ValueError("unrecognized mode '%s'" % mode)
+    if not hasattr(OPinv, "solve_dev"):
+        raise TypeError("OPinv must be an eigd_b200.SpLuOperator (device factorisation); got %r" % type(OPinv))
+    if ncv is None:
+        ncv = min(n, max(2 * k + 1, 20))
+    if ncv > n or ncv <= k:
+        raise ValueError("ncv must be k<ncv<=n")
+    st = lanczos_thick_restart(Bip, OPinv, k, ncv, float(sigma), mode=mode, tol=float(tol), maxiter=maxiter, v0=v0, seed=seed)
+    if not return_eigenvectors:
+        return st.d
+    out = (st.d, to_host(st.Z), st.T, to_host(st.Vt).T.copy() if not return_state else None)
+    if return_state:
+        return out + (st,)
+    return out

@@ -192,6 +192,8 @@ __global__ void col_scale_kernel(int64_t n, int k, int mode, const double* __res
     double f = s[c];
     if (mode == 1) f = 1.0 / f;
     else if (mode == 2) f = 1.0 / sqrt(f);
+    else if (mode == 3) f = (f > 0.0) ? 1.0 / sqrt(f) : 0.0;   // safe normalisation (converged / empty columns)
+    else if (mode == 4) f = (f != 0.0) ? 1.0 / f : 0.0;
     X[i * xrs + (int64_t)c * xcs] *= f;
   }
 }

@@ -257,3 +257,58 @@ extern "C" int eigd_node_gather(int nnodes, const int* d_nptr, const int* d_nele
   EIGD_CHECK_LAUNCH();
   return 0;
 }
+
+// ---- element density and material interpolation ----------------------------------------------
+// rhoE[e] = 1/4 sum_a rho[conn[e, a]]          (examples/thermal.py:348-353, natural_frequency.py:399-404)
+// law 0 (thermal.py:132,198,175-188,236-244): ks = k0((1-b) r^p + b), ms = c0((1-b) r + b)
+// law 1 (natural_frequency.py:140-143,219-220 "simp"): ks = r^p + r0, ms = c0 r
+// law 2 (RAMP, natural_frequency.py:142-143): ks = r/(1+q(1-r)) + r0, ms = c0 r
+// par = {p or q, k0, c0, b or r0}
+namespace {
+__global__ void q4_material_kernel(int law, int nelems, const int* __restrict__ conn, const double* __restrict__ rho,
+                                   double p0, double k0, double c0, double b, double* __restrict__ rhoE,
+                                   double* __restrict__ ks, double* __restrict__ ms, double* __restrict__ dk,
+                                   double* __restrict__ dm) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nelems) return;
+  double r;
+  if (conn) {
+    r = 0.25 * (rho[conn[4 * e]] + rho[conn[4 * e + 1]] + rho[conn[4 * e + 2]] + rho[conn[4 * e + 3]]);
+    if (rhoE) rhoE[e] = r;
+  } else {
+    r = rho[e];
+  }
+  double vk, vm, gk, gm;
+  if (law == 0) {
+    vk = k0 * ((1.0 - b) * pow(r, p0) + b);
+    gk = (1.0 - b) * k0 * p0 * pow(r, p0 - 1.0);
+    vm = c0 * ((1.0 - b) * r + b);
+    gm = (1.0 - b) * c0;
+  } else if (law == 1) {
+    vk = k0 * pow(r, p0) + b;
+    gk = k0 * p0 * pow(r, p0 - 1.0);
+    vm = c0 * r;
+    gm = c0;
+  } else {
+    double den = 1.0 + p0 * (1.0 - r);
+    vk = k0 * r / den + b;
+    gk = k0 * (1.0 + p0) / (den * den);
+    vm = c0 * r;
+    gm = c0;
+  }
+  if (ks) ks[e] = vk;
+  if (ms) ms[e] = vm;
+  if (dk) dk[e] = gk;
+  if (dm) dm[e] = gm;
+}
+}  // namespace
+
+extern "C" int eigd_q4_material(int law, int nelems, const int* d_conn, const double* d_rho, const double* par4,
+                                double* d_rhoE, double* d_ks, double* d_ms, double* d_dk, double* d_dm) {
+  if (nelems <= 0) return 0;
+  if (law < 0 || law > 2) { eigd_set_error("q4_material: unknown law %d", law); return 1; }
+  EIGD_LAUNCH(q4_material_kernel, (nelems + 255) / 256, 256, 0, law, nelems, d_conn, d_rho, par4[0], par4[1], par4[2],
+              par4[3], d_rhoE, d_ks, d_ms, d_dk, d_dm);
+  EIGD_CHECK_LAUNCH();
+  return 0;
+}

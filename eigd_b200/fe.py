@@ -1,0 +1,248 @@
+"""Device-side finite-element operators for the Q4 problems of the reference examples.
+
+Host part (numpy, runs once per mesh): mesh numbering, DOF maps, the CSR pattern of K/M and the
+integer assembly maps (element, a, b) -> CSR non-zero, node -> element adjacency, the conic
+filter pattern.  Device part (kernels of csrc/fe.cu): material interpolation, gather-form
+assembly of K and M, the bilinear sensitivity forms ``w^T (dK/drho_e) v`` / ``w^T (dM/drho_e) v``
+summed over modes, element -> node gather, filter products.
+
+Mirrors (paths relative to the reference root):
+  mesh / connectivity       examples/thermal.py:1475-1498, examples/natural_frequency.py:850-894
+  DOF map and COO lists     examples/thermal.py:79-92, examples/natural_frequency.py:90-104
+  K, M assembly             examples/thermal.py:126-148,192-214, examples/natural_frequency.py:134-160,205-236
+  dK, dM callbacks          examples/thermal.py:150-190,216-246, examples/natural_frequency.py:162-203,238-284
+  node scatter              examples/thermal.py:612-615
+  node filter               examples/node_filter.py:61-88 (construction), :164-217 (apply / gradient)
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import device as D
+from ._hostdev import is_dev, to_dev, to_host, like_input
+
+
+def grid_mesh(nx, ny, Lx=1.0, Ly=1.0):
+    """Structured Q4 mesh with the examples' numbering: node(i, j) = i*(ny+1) + j,
+    element e = i + nx*j, counter-clockwise connectivity (examples/thermal.py:1475-1498)."""
+    nodes = np.arange((nx + 1) * (ny + 1), dtype=np.int64).reshape(nx + 1, ny + 1)
+    X = np.zeros(((nx + 1) * (ny + 1), 2))
+    X[:, 0] = np.repeat(np.linspace(0, Lx, nx + 1), ny + 1)
+    X[:, 1] = np.tile(np.linspace(0, Ly, ny + 1), nx + 1)
+    conn = np.empty((nx * ny, 4), dtype=np.int64)
+    conn[:, 0] = nodes[:-1, :-1].T.ravel()
+    conn[:, 1] = nodes[1:, :-1].T.ravel()
+    conn[:, 2] = nodes[1:, 1:].T.ravel()
+    conn[:, 3] = nodes[:-1, 1:].T.ravel()
+    return conn, X
+
+
+def element_dofs(conn, dof):
+    """var[e] = the element's global DOF list (examples/natural_frequency.py:90-92)."""
+    conn = np.asarray(conn, dtype=np.int64)
+    return (conn[:, :, None] * dof + np.arange(dof)[None, None, :]).reshape(conn.shape[0], -1)
+
+
+def assembly_structure(var, ndof):
+    """CSR pattern of sum_e P_e^T K_e P_e plus, for every non-zero, the list of (e, a, b) sources.
+
+    The (i, j) lists are in ``Ke.flatten()`` order (examples/natural_frequency.py:94-104) and the
+    CSR is what ``coo_matrix((vals, (i, j))).tocsr()`` produces (:157-158): duplicates summed,
+    column indices sorted.  Returns indptr (int32), indices (int32), src_ptr (int64, nnz+1),
+    src (int64, flat COO positions e*ne*ne + a*ne + b grouped by non-zero, ascending)."""
+    ne = var.shape[1]
+    i = np.repeat(var, ne, axis=1).ravel()
+    j = np.tile(var, (1, ne)).ravel()
+    key = i * np.int64(ndof) + j
+    order = np.argsort(key, kind="stable")
+    skey = key[order]
+    first = np.ones(len(skey), dtype=bool)
+    first[1:] = skey[1:] != skey[:-1]
+    ukey = skey[first]
+    rows = (ukey // ndof).astype(np.int64)
+    indices = (ukey % ndof).astype(np.int32)
+    indptr = np.zeros(ndof + 1, dtype=np.int64)
+    np.add.at(indptr, rows + 1, 1)
+    indptr = np.cumsum(indptr).astype(np.int32)
+    src_ptr = np.concatenate([np.nonzero(first)[0], [len(skey)]]).astype(np.int64)
+    return indptr, indices, src_ptr, order.astype(np.int64)
+
+
+def node_adjacency(conn, nnodes):
+    """CSR node -> elements (gather form of the ``np.add.at`` scatter, examples/thermal.py:612-615)."""
+    conn = np.asarray(conn, dtype=np.int64)
+    e = np.repeat(np.arange(conn.shape[0], dtype=np.int64), conn.shape[1])
+    v = conn.ravel()
+    order = np.lexsort((e, v))
+    nptr = np.zeros(nnodes + 1, dtype=np.int64)
+    np.add.at(nptr, v + 1, 1)
+    return np.cumsum(nptr).astype(np.int32), e[order].astype(np.int32)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class _Half:
+    """One of the two reference callbacks ``dAdx(w, v)`` / ``dBdx(w, v)``."""
+
+    def __init__(self, parent, which):
+        self.parent, self.which = parent, which
+        self.fused_with = None
+
+    def device_call(self, W, V):
+        if self.which == "A":
+            return self.parent.device_call_fused(W, None, V, 1.0, 0.0)
+        return self.parent.device_call_fused(None, W, V, 0.0, 1.0)
+
+    def __call__(self, w, v):
+        out = self.device_call(to_dev(w), to_dev(v))
+        return like_input(out, w)
+
+
+class Q4Problem:
+    """Thermal (1 DOF/node) or plane-stress (2 DOF/node) Q4 model with its operators in HBM.
+
+    kind "thermal": K_e = kappa(rho_e) sum_q detJ Be^T Be, M_e = c(rho_e) sum_q detJ N N^T
+      with kappa = kappa0((1-beta) rho^p + beta), c = cp*density*((1-beta) rho + beta)
+      (examples/thermal.py:23-28,132,198).
+    kind "plane_stress": K_e = s(rho_e) sum_q detJ Be^T C0 Be, M_e = density*rho_e sum_q detJ He^T He
+      with s = rho^p + rho0_K (SIMP) or rho/(1+q(1-rho)) + rho0_K (RAMP)
+      (examples/natural_frequency.py:83-86,140-155,219-231).
+    """
+
+    def __init__(self, conn, X, kind="thermal", E=1.0, nu=0.3, kappa=1.0, density=1.0, heat_capacity=1.0, p=3.0,
+                 beta=1e-6, rho0_K=1e-6, ptype_K="simp", q=5.0):
+        if kind not in ("thermal", "plane_stress"):
+            raise ValueError("unknown kind %r" % kind)
+        dev = D.dev()
+        self.kind = kind
+        self.kid = 0 if kind == "thermal" else 1
+        self.conn = np.asarray(conn, dtype=np.int64)
+        self.X = np.asarray(X, dtype=np.float64)
+        self.nelems = self.conn.shape[0]
+        self.nnodes = int(self.conn.max()) + 1
+        self.dof = 1 if kind == "thermal" else 2
+        self.ndof = self.dof * self.nnodes
+        self.var = element_dofs(self.conn, self.dof)
+        self.indptr, self.indices, src_ptr, src = assembly_structure(self.var, self.ndof)
+        self.nnz = len(self.indices)
+        nptr, nelem = node_adjacency(self.conn, self.nnodes)
+        if kind == "thermal":
+            self.law, self.par = 0, np.array([p, kappa, heat_capacity * density, beta])
+        elif ptype_K == "simp":
+            self.law, self.par = 1, np.array([p, 1.0, density, rho0_K])
+        elif ptype_K == "ramp":
+            self.law, self.par = 2, np.array([q, 1.0, density, rho0_K])
+        else:
+            raise ValueError("unknown ptype_K %r" % ptype_K)
+        C0 = E * np.array([[1.0, nu, 0.0], [nu, 1.0, 0.0], [0.0, 0.0, 0.5 * (1.0 - nu)]]) / (1.0 - nu**2)
+        self.C0 = C0
+        # ---- device mirrors -------------------------------------------------------------
+        self.conn_d = torch.as_tensor(self.conn.astype(np.int32), device=dev)
+        self.xy_d = to_dev(self.X)
+        self.cmat6_d = to_dev(np.array([C0[0, 0], C0[0, 1], C0[0, 2], C0[1, 1], C0[1, 2], C0[2, 2]]))
+        self.indptr_d = torch.as_tensor(self.indptr, device=dev)
+        self.indices_d = torch.as_tensor(self.indices, device=dev)
+        self.src_ptr_d = torch.as_tensor(src_ptr, device=dev)
+        self.src_d = torch.as_tensor(src, device=dev)
+        self.nptr_d = torch.as_tensor(nptr, device=dev)
+        self.nelem_d = torch.as_tensor(nelem, device=dev)
+        self.rhoE_d = D.empty(self.nelems)
+        self.ks_d, self.ms_d = D.empty(self.nelems), D.empty(self.nelems)
+        self.dk_d, self.dm_d = D.empty(self.nelems), D.empty(self.nelems)
+        self._par_c = (ctypes.c_double * 4)(*[float(v) for v in self.par])
+        self.dAdx, self.dBdx = _Half(self, "A"), _Half(self, "B")
+        self.dAdx.fused_with, self.dBdx.fused_with = self.dBdx, self.dAdx
+
+    # ---- material -----------------------------------------------------------------------------
+    def set_density(self, rho=None, rhoE=None):
+        """Nodal density rho (filtered design) -> element density + material factors, or set the
+        element densities directly."""
+        lib = _lib.load()
+        if rhoE is not None:
+            self.rhoE_d.copy_(to_dev(rhoE))
+            _lib.check(lib.eigd_q4_material(self.law, self.nelems, None, _ptr(self.rhoE_d), self._par_c, None,
+                                            _ptr(self.ks_d), _ptr(self.ms_d), _ptr(self.dk_d), _ptr(self.dm_d)), "q4_material")
+        else:
+            rho_d = to_dev(rho)
+            _lib.check(lib.eigd_q4_material(self.law, self.nelems, _ptr(self.conn_d), _ptr(rho_d), self._par_c,
+                                            _ptr(self.rhoE_d), _ptr(self.ks_d), _ptr(self.ms_d), _ptr(self.dk_d),
+                                            _ptr(self.dm_d)), "q4_material")
+        return self.rhoE_d
+
+    # ---- assembly -------------------------------------------------------------------------------
+    def assemble(self):
+        """K(rho), M(rho) as CsrDevice sharing one pattern (values computed in gather form)."""
+        Kv, Mv = D.empty(self.nnz), D.empty(self.nnz)
+        D.q4_assemble(self.kid, self.conn_d, self.xy_d, self.ks_d, self.ms_d, self.cmat6_d, self.src_ptr_d, self.src_d,
+                      self.nnz, Kv, Mv)
+        shape = (self.ndof, self.ndof)
+        K = D.CsrDevice(self.indptr_d, self.indices_d, Kv, shape)
+        M = D.CsrDevice(self.indptr_d, self.indices_d, Mv, shape)
+        return K, M
+
+    def dof_coords(self):
+        """Node coordinates for geometric nested dissection (``SpLuOperator(coords=..., dof_per_node=...)``)."""
+        return self.X, self.dof
+
+    # ---- sensitivities ----------------------------------------------------------------------------
+    def device_call_fused(self, WA, WB, V, cA, cB):
+        """cA * sum_k WA_k^T (dK/drho_e) V_k + cB * sum_k WB_k^T (dM/drho_e) V_k per element (device)."""
+        V2 = V if V.dim() == 2 else V.unsqueeze(1)
+        WA2 = None if WA is None else (WA if WA.dim() == 2 else WA.unsqueeze(1))
+        WB2 = None if WB is None else (WB if WB.dim() == 2 else WB.unsqueeze(1))
+        V2 = V2 if V2.is_contiguous() else V2.contiguous()
+        WA2 = None if WA2 is None else (WA2 if WA2.is_contiguous() else WA2.contiguous())
+        WB2 = None if WB2 is None else (WB2 if WB2.is_contiguous() else WB2.contiguous())
+        out = D.zeros(self.nelems)
+        D.q4_quadforms(self.kid, self.conn_d, self.xy_d, self.cmat6_d, WA2, WB2, V2, self.dk_d, self.dm_d,
+                       float(cA), -float(cB), out)
+        return out
+
+    def scatter_to_nodes(self, evals, scale=0.25):
+        """rho_b[v] = scale * sum_{e ni v} evals[e] (examples/thermal.py:612-615)."""
+        ev = to_dev(evals)
+        out = D.empty(self.nnodes)
+        D.node_gather(self.nptr_d, self.nelem_d, ev, scale, out)
+        return like_input(out, evals)
+
+
+class NodeFilter:
+    """Conic node filter F[i, j] ~ max(0, r0 - |X_i - X_j|), rows normalised to 1
+    (examples/node_filter.py:61-88), applied on the device as CSR products (:164-217).
+    Spatial filter without design-variable map or projection (the form the C1/C2/C5 models use)."""
+
+    ftype = "spatial"
+
+    def __init__(self, conn, X, r0=1.0, ftype="spatial", dvmap=None, num_design_vars=None, beta=10.0, eta=0.5,
+                 projection=False):
+        from scipy import sparse, spatial
+        if ftype != "spatial":
+            raise NotImplementedError("only the spatial (conic) filter is implemented")
+        if dvmap is not None or projection:
+            raise NotImplementedError("dvmap / projection are not implemented on the device filter")
+        self.X = np.asarray(X, dtype=np.float64)
+        self.nnodes = self.X.shape[0]
+        self.r0 = r0
+        self.num_design_vars = self.nnodes
+        tree = spatial.cKDTree(self.X)
+        Dm = tree.sparse_distance_matrix(tree, r0, output_type="coo_matrix")
+        w = r0 - Dm.data
+        F = sparse.coo_matrix((w, (Dm.row, Dm.col)), shape=(self.nnodes, self.nnodes)).tocsr()
+        rs = np.asarray(F.sum(axis=1)).ravel()
+        F = (sparse.diags(1.0 / rs) @ F).tocsr()
+        F.sort_indices()
+        FT = F.T.tocsr()
+        FT.sort_indices()
+        self.F, self.FT = F, FT
+        self.F_d = D.CsrDevice.from_scipy(F)
+        self.FT_d = D.CsrDevice.from_scipy(FT)
+
+    def apply(self, x):
+        return like_input(self.F_d.spmm(to_dev(x)), x)
+
+    def apply_gradient(self, g, x=None, rho=None):
+        return like_input(self.FT_d.spmm(to_dev(g)), g)

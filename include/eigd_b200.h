@@ -60,7 +60,8 @@ int eigd_col_dot(int64_t n, int k, const double* d_X, int64_t xrs, int64_t xcs,
 /* Y[i,c] += sign * s[c] * X[i,c]   (s on device) */
 int eigd_col_axpy(int64_t n, int k, double sign, const double* d_s, const double* d_X, int64_t xrs, int64_t xcs,
                   double* d_Y, int64_t yrs, int64_t ycs);
-/* X[i,c] *= s[c]  (mode 0)   or   X[i,c] /= s[c]  (mode 1)   or X[i,c] /= sqrt(s[c]) (mode 2) */
+/* X[i,c] *= s[c]  (mode 0)   or   X[i,c] /= s[c]  (mode 1)   or X[i,c] /= sqrt(s[c]) (mode 2);
+ * modes 3 / 4 are the zero-safe forms of 2 / 1 (a zero scale leaves a zero column) */
 int eigd_col_scale(int64_t n, int k, int mode, const double* d_s, double* d_X, int64_t xrs, int64_t xcs);
 /* Y[i,c] = X[i,c] (strided copy / transpose) */
 int eigd_copy2d(int64_t n, int k, const double* d_X, int64_t xrs, int64_t xcs, double* d_Y, int64_t yrs, int64_t ycs);
@@ -121,6 +122,12 @@ int eigd_q4_assemble(int kind, int nelems, const int* d_conn, const double* d_xy
 int eigd_q4_quadforms(int kind, int nelems, const int* d_conn, const double* d_xy, const double* d_cmat6,
                       const double* d_WA, const double* d_WB, const double* d_V, int N, int ldw,
                       const double* d_dk, const double* d_dm, double sA, double sB, double* d_out);
+/* Element density rhoE[e] = 1/4 sum_a rho[conn[e,a]] (d_conn NULL: d_rho is already per element) and the
+ * penalised material factors / derivatives of the examples (thermal.py:132,175-188,198,236-244;
+ * natural_frequency.py:140-143,198-201,219-220).  law 0 thermal SIMP, 1 structural SIMP, 2 RAMP;
+ * par4 = {p or q, k0, c0, beta or rho0} (host).  Any output may be NULL. */
+int eigd_q4_material(int law, int nelems, const int* d_conn, const double* d_rho, const double* par4,
+                     double* d_rhoE, double* d_ks, double* d_ms, double* d_dk, double* d_dm);
 /* node_out[v] = scale * sum_{e in adj(v)} e_vals[e]   (gather form of np.add.at, thermal.py:612-615) */
 int eigd_node_gather(int nnodes, const int* d_nptr, const int* d_nelem, const double* d_evals, double scale, double* d_out);
 

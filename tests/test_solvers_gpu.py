@@ -1,0 +1,258 @@
+"""Parity of the device eigensolvers / adjoint solvers / total derivative (through the public API of
+eigd_b200, i.e. through the C-ABI) against the frozen outputs of the unmodified reference
+(tests/golden/*.npz) and against the CPU oracle on the same inputs.
+
+Tolerances (BASELINE.json north_star): eigenvalues 1e-10 relative, sign-aligned eigenvectors,
+adjoints and df/dx 1e-8 relative, fp64."""
+import warnings
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, corr_from_array, align_signs
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+def rel(a, b):
+    return np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(b).max(), 1e-300)
+
+
+@pytest.fixture(scope="module")
+def E():
+    import eigd_b200
+    from eigd_b200 import device
+    device.init()
+    return eigd_b200
+
+
+def shifted(g, mode="normal"):
+    A, B, sigma = g["A"], g["B"], float(g["sigma"])
+    return (A - sigma * B).tocsc() if mode == "normal" else (B + sigma * A).tocsc()
+
+
+@pytest.fixture(scope="module")
+def th():
+    return load_golden("thermal_basiclanczos")
+
+
+@pytest.fixture(scope="module")
+def th_solver(E, th):
+    f = E.SpLuOperator(shifted(th))
+    s = E.BasicLanczos(N=int(th["N"]), m=int(th["m_max"]), tol=1e-14)
+    lam, Phi = s.solve(th["A"], th["B"], f, float(th["sigma"]))
+    return s, f, lam, Phi
+
+
+def test_splu_operator_semantics(E, th):
+    mat = shifted(th)
+    f = E.SpLuOperator(mat)
+    n = mat.shape[0]
+    assert f.shape == (n, n) and f.dtype == np.float64 and f.count == 0
+    rng = np.random.default_rng(0)
+    b = rng.normal(size=n)
+    x = f(b)
+    assert isinstance(x, np.ndarray) and x.shape == (n,)
+    assert np.abs(mat @ x - b).max() / np.abs(b).max() < 1e-12
+    assert f.count == 1
+    Bm = rng.normal(size=(n, 7))
+    Xm = f @ Bm
+    assert np.abs(mat @ Xm - Bm).max() / np.abs(Bm).max() < 1e-12
+    assert f.count == 8                                     # one count per right-hand-side column
+    f.count = 0
+    Xd = f(torch.as_tensor(Bm, device="cuda"))
+    assert isinstance(Xd, torch.Tensor) and rel(Xd.cpu().numpy(), Xm) < 1e-13 and f.count == 7
+
+
+def test_basic_lanczos_vs_reference(E, th, th_solver):
+    s, f, lam, Phi = th_solver
+    assert rel(lam, th["lam"]) < 1e-10
+    Pa, _ = align_signs(Phi, th["Phi"])
+    assert rel(Pa, th["Phi"]) < 1e-8
+    assert (s.indices == th["indices"]).all()
+    assert s.m == int(th["m"])
+    # Lanczos invariants: V^T B V = I, V^T B OP V = T
+    V = s.V[:, :s.m]
+    B = th["B"]
+    assert np.abs(V.T @ (B @ V) - np.eye(s.m)).max() < 1e-11
+    assert rel(s.alpha[:10], th["alpha"][:10]) < 1e-8
+
+
+@pytest.mark.parametrize("method", ["sibk", "laa", "dl", "pcpg", "pgmres"])
+def test_adjoint_methods_vs_reference(E, th, th_solver, method):
+    s, f, lam, Phi = th_solver
+    # same sign convention as the golden run (BasicLanczos is deterministic up to rounding)
+    _, sgn = align_signs(Phi, th["Phi"])
+    assert (sgn > 0).all()
+    kw = {} if method in ("laa", "dl") else {"rtol": 1e-12}
+    res_hist = []
+    if method == "sibk":
+        kw["callback"] = res_hist.append
+    f.count = 0
+    psi, data = s.solve_adjoint(th["Phib"].copy(), method=method, **kw)
+    assert rel(psi, th["psi_" + method]) < 1e-8
+    assert set(data) == set(corr_from_array(th["corr_" + method]))
+    if method == "dl":
+        assert f.count == int(th["nsolves_" + method])      # same number of preconditioner applications
+    if method == "sibk":                                    # lock step: converged modes ride along until the last one stops
+        assert f.count >= int(th["nsolves_" + method])
+    if method == "sibk":
+        assert len(res_hist) > s.N
+    if method != "laa":
+        res, orth = s.eval_adjoint_residual_norm(th["Phib"], psi, b_ortho=False)
+        assert rel(res, th["res_" + method]) < 1e-3 or res.max() < 1e-9
+
+
+def test_total_derivative_vs_reference(E, th, th_solver):
+    from eigd_b200 import fe
+    s, f, lam, Phi = th_solver
+    prob = fe.Q4Problem(th["conn"], th["X"], "thermal")
+    prob.set_density(rhoE=th["rhoE"])
+    # assembly: integer structure bit-exact, values to rounding
+    assert (prob.indptr == th["A_indptr"]).all() and (prob.indices == th["A_indices"]).all()
+    K, M = prob.assemble()
+    assert rel(K.data.cpu().numpy(), th["A_data"]) < 1e-13 and rel(M.data.cpu().numpy(), th["B_data"]) < 1e-13
+    data = corr_from_array(th["corr_sibk"])
+    for deriv_type in ("tensor", "vector"):
+        dfdx = np.zeros(prob.nelems)
+        out = s.add_total_derivative(th["lamb"], th["Phib"], th["psi_sibk"], prob.dAdx, prob.dBdx, dfdx,
+                                     adj_corr_data=data, deriv_type=deriv_type)
+        assert out is dfdx
+        assert rel(dfdx, th["dfdx_sibk"]) < 1e-8
+    # plain python callbacks (the reference's calling convention) give the same numbers
+    import fe_oracle as fo
+    mdl = fo.Q4Model(th["conn"], th["X"], "thermal")
+    d2 = np.zeros(prob.nelems)
+    E.add_eig_total_derivative(th["lam"], th["Phi"], th["lamb"], th["Phib"], th["psi_sibk"],
+                               lambda w, v: mdl.dK(th["rhoE"], w, v), lambda w, v: mdl.dM(th["rhoE"], w, v), d2,
+                               adj_corr_data=data, deriv_type="tensor")
+    assert rel(d2, th["dfdx_sibk"]) < 1e-8
+    flt = fe.NodeFilter(th["conn"], th["X"], r0=float(th["r0"]))
+    xb = flt.apply_gradient(prob.scatter_to_nodes(dfdx))
+    assert rel(xb, th["xb_sibk"]) < 1e-8
+
+
+def test_iram_vs_reference(E):
+    g = load_golden("thermal_iram")
+    f = E.SpLuOperator(shifted(g))
+    s = E.IRAM(N=int(g["N"]), m=int(g["m"]))
+    s.seed = 1
+    lam, Phi = s.solve(g["A"], g["B"], f, float(g["sigma"]))
+    scale = np.abs(g["lam"]).max()
+    assert np.abs(lam - g["lam"]).max() < 1e-10 * scale
+    Pa, sgn = align_signs(Phi, g["Phi"])
+    assert rel(Pa[:, 1:], g["Phi"][:, 1:]) < 1e-8
+    # invariants the adjoint code relies on (last card)
+    V, B = s.V, g["B"]
+    m = s.m
+    assert np.abs(V.T @ (B @ V) - np.eye(m)).max() < 1e-11
+    import scipy.sparse.linalg as spla
+    lu = spla.splu(shifted(g))
+    OPV = np.column_stack([lu.solve(B @ V[:, j]) for j in range(m)])
+    assert np.abs(V.T @ (B @ OPV) - s.T).max() < 1e-9 * np.abs(s.T).max()
+    for i in range(s.N):
+        assert rel(V @ s.Y[:, s.indices[i]], Phi[:, i]) < 1e-10
+    # adjoint in the golden sign convention
+    psi, data = s.solve_adjoint(g["Phib"] * sgn, method="sibk", rtol=1e-12)
+    assert rel(psi * sgn, g["psi_sibk"]) < 1e-8
+    from eigd_b200 import fe
+    prob = fe.Q4Problem(g["conn"], g["X"], "thermal")
+    prob.set_density(rhoE=g["rhoE"])
+    dfdx = np.zeros(prob.nelems)
+    s.add_total_derivative(g["lamb"], g["Phib"] * sgn, psi, prob.dAdx, prob.dBdx, dfdx, adj_corr_data=data, deriv_type="tensor")
+    assert rel(dfdx, g["dfdx_sibk"]) < 1e-8
+
+
+def test_buckling_vs_reference(E):
+    g = load_golden("buckling_basiclanczos")
+    f = E.SpLuOperator(shifted(g, "buckling"))
+    s = E.BasicLanczos(N=int(g["N"]), m=int(g["m_max"]), tol=1e-14, mode="buckling")
+    lam, Phi = s.solve(g["A"], g["B"], f, float(g["sigma"]))
+    assert rel(lam, g["lam"]) < 1e-10
+    Pa, sgn = align_signs(Phi, g["Phi"])
+    assert rel(Pa, g["Phi"]) < 1e-8
+    # sibk reproduces the reference to rounding; pcpg on this ill-conditioned pencil is only reproducible to
+    # ~1e-7 (the reference's own sibk and pcpg answers differ by 2.6e-8, measured on the fixture)
+    for method, tol in (("sibk", 1e-9), ("pcpg", 1e-6)):
+        psi, data = s.solve_adjoint(g["Phib"] * sgn, method=method, rtol=1e-12)
+        assert rel(psi * sgn, g["psi_" + method]) < tol
+    # IRAM in buckling mode reaches the same eigenvalues
+    s2 = E.IRAM(N=int(g["N"]), m=24, mode="buckling")
+    s2.seed = 3
+    lam2, Phi2 = s2.solve(g["A"], g["B"], f, float(g["sigma"]))
+    assert rel(lam2, g["lam"]) < 1e-10
+
+
+def test_nf_iram_gradient_vs_reference(E):
+    from eigd_b200 import fe
+    g = load_golden("nf_iram")
+    A, B, sigma = g["A"], g["B"], float(g["sigma"])
+    f = E.SpLuOperator(shifted(g))
+    Ncomp, N = int(g["Ncomp"]), int(g["N"])
+    s = E.IRAM(N=Ncomp, m=int(g["m"]))
+    s.seed = 5
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        lam, Phi = s.solve(A, B, f, sigma)
+    scale = np.abs(g["lam_all"]).max()
+    assert np.abs(lam - g["lam_all"]).max() < 1e-10 * scale
+    Pa, sgn = align_signs(Phi[:, 3:], g["Phi_all"][:, 3:])
+    assert rel(Pa, g["Phi_all"][:, 3:]) < 1e-8
+    R0, R1 = Phi[:, :3], g["Phi_all"][:, :3]                       # rigid-body triple: compare as a subspace
+    assert np.abs(R0 @ (R0.T @ (B @ R1)) - R1).max() < 1e-8 * np.abs(R1).max()
+    # gradient, following examples/natural_frequency.py:442-514 (three zero columns for the rigid modes)
+    n = A.shape[0]
+    Q0b = np.zeros((n, Ncomp))
+    Q0b[:, 3:] = g["Phib"] * sgn
+    psi0, data = s.solve_adjoint(Q0b, method="sibk", rtol=1e-12, lanczos_guess=True, update_guess=False, bs_target=1)
+    assert rel(psi0[:, 3:] * sgn, g["psi"]) < 1e-8
+    data0 = {i: [(j, xi, eta) for (j, xi, eta) in items if j >= 3] for i, items in data.items() if i >= 3}
+    data0 = {i: v for i, v in data0.items() if v}
+    lamb0 = np.zeros(Ncomp)
+    lamb0[3:] = g["lamb"]
+    prob = fe.Q4Problem(g["conn"], g["X"], "plane_stress")
+    prob.set_density(rhoE=g["rhoE"])
+    assert (prob.indptr == g["A_indptr"]).all() and (prob.indices == g["A_indices"]).all()
+    K, M = prob.assemble()
+    assert rel(K.data.cpu().numpy(), g["A_data"]) < 1e-12 and rel(M.data.cpu().numpy(), g["B_data"]) < 1e-12
+    dfdx = np.zeros(prob.nelems)
+    s.add_total_derivative(lamb0, Q0b, psi0, prob.dAdx, prob.dBdx, dfdx, adj_corr_data=data0, deriv_type="tensor")
+    assert rel(dfdx, g["dfdx"]) < 1e-8
+
+
+def test_device_resident_path_matches_host_path(E, th):
+    """torch-in / torch-out fast path == numpy path."""
+    from eigd_b200 import device as D
+    Ad, Bd = D.CsrDevice.from_scipy(th["A"]), D.CsrDevice.from_scipy(th["B"])
+    sigma = float(th["sigma"])
+    vals = D.axpby(1.0, Ad.data, -sigma, Bd.data)
+    f = E.SpLuOperator(Ad.with_values(vals))
+    s = E.IRAM(N=int(th["N"]), m=30)
+    s.seed = 2
+    lam, Phi = s.solve(Ad, Bd, f, sigma)
+    assert np.abs(lam - th["lam"]).max() < 1e-10 * np.abs(th["lam"]).max()
+    _, sgn = align_signs(Phi, th["Phi"])
+    Phib_d = torch.as_tensor(th["Phib"] * sgn, device="cuda")
+    psi_d, data = s.solve_adjoint(Phib_d, method="sibk", rtol=1e-12)
+    assert isinstance(psi_d, torch.Tensor)
+    assert rel(psi_d.cpu().numpy()[:, 1:] * sgn[1:], th["psi_sibk"][:, 1:]) < 1e-7
+
+
+def test_error_behaviour(E, th, th_solver):
+    s, f, lam, Phi = th_solver
+    n = th["A"].shape[0]
+    with pytest.raises(ValueError, match="Unknown method"):
+        s.solve_adjoint(th["Phib"], method="nope")
+    with pytest.raises(ValueError, match="Unknown mode"):
+        E.IRAM(mode="nope")
+    with pytest.raises(ValueError, match="Initial guess must have the shape"):
+        s.solve_adjoint(th["Phib"], psi=np.zeros((n, 2)))
+    with pytest.raises(ValueError, match="Eigenvalues must be of length"):
+        E.add_eig_total_derivative(lam[:-1], Phi, th["lamb"], th["Phib"], th["psi_sibk"], None, None, np.zeros(3))
+    with pytest.raises(ValueError, match="A must have dimensions"):
+        E.IRAM().solve(th["A"][:, :-1], th["B"], f, 0.0)
+    with pytest.raises(TypeError):
+        import scipy.sparse.linalg as spla
+        E.IRAM(N=3).solve(th["A"], th["B"], spla.aslinearoperator(th["A"]), 0.0)   # no CPU factor fallback
