@@ -11,6 +11,10 @@ import torch
 from . import device as D
 
 
+# bytes moved across PCIe by the public API since the last reset (bench.py "e2e" accounting)
+XFER = {"h2d": 0, "d2h": 0}
+
+
 def is_dev(x):
     return isinstance(x, torch.Tensor)
 
@@ -27,6 +31,7 @@ def as_csr_device(A):
     if base is not None and hasattr(base, "tocsr"):
         A = base
     if hasattr(A, "tocsr"):
+        XFER["h2d"] += A.nnz * 12 + (A.shape[0] + 1) * 4
         return D.CsrDevice.from_scipy(A)
     raise TypeError("eigd_b200 needs a scipy sparse matrix or a device.CsrDevice, got %r (there is no "
                     "dense / LinearOperator CPU fallback)" % type(A))
@@ -40,10 +45,12 @@ def to_dev(x, copy=False):
     a = np.asarray(x)
     if np.iscomplexobj(a):
         raise NotImplementedError("eigd_b200: complex (complex-step) operands are not supported on the device path")
+    XFER["h2d"] += a.size * 8
     return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device=D.dev())
 
 
 def to_host(t):
+    XFER["d2h"] += t.numel() * t.element_size()
     return t.detach().cpu().numpy()
 
 
@@ -53,4 +60,5 @@ def like_input(t, ref):
 
 
 def small_to_dev(a):
+    XFER["h2d"] += np.size(a) * 8
     return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device=D.dev())

@@ -37,6 +37,8 @@ SIGNATURES = {
     "eigd_symbolic_assembly_map_host": (c_int, [c_ptr, c_int, c_ptr, c_ptr, c_ptr]),
     "eigd_symbolic_assembly_map_device": (c_int, [c_ptr, c_int, c_ptr, c_ptr, c_ptr]),
     "eigd_factor_create": (c_int, [c_ptr, c_int, c_ptr]),
+    "eigd_factor_workspace_bytes": (c_i64, [c_ptr, c_int]),
+    "eigd_factor_create_in": (c_int, [c_ptr, c_int, c_ptr, c_i64, c_ptr]),
     "eigd_factor_destroy": (None, [c_ptr]),
     "eigd_factor_numeric": (c_int, [c_ptr, c_i64, c_ptr, c_ptr]),
     "eigd_factor_info": (c_int, [c_ptr, c_ptr]),

@@ -639,6 +639,8 @@ struct eigd_factor {
   double piv_tol = 1e-11;
   int64_t bytes = 0;
   bool attrs_set = false;
+  char* base = nullptr;
+  bool owns = true;
 };
 
 extern "C" int eigd_symbolic_assembly_map_device(eigd_symbolic* s, int n, const int* d_indptr, const int* d_indices,
@@ -660,36 +662,78 @@ extern "C" int eigd_symbolic_assembly_map_device(eigd_symbolic* s, int n, const 
   return 0;
 }
 
-extern "C" int eigd_factor_create(eigd_symbolic* s, int max_rhs, eigd_factor** out) {
+static inline int64_t align256(int64_t b) { return (b + 255) / 256 * 256; }
+
+// sizes (bytes, 256-aligned) of the eight device arrays of a factor, in carving order
+static void factor_layout(const eigd_symbolic* s, int64_t linv_total, int max_rhs, int64_t sz[8]) {
+  int64_t nfront = s->front_off[s->nsuper], sumf = s->w_off[s->nsuper];
+  sz[0] = align256(nfront * 8);                        // fronts
+  sz[1] = align256(linv_total * 8);                    // linv
+  sz[2] = align256((int64_t)s->n * 8);                 // dval
+  sz[3] = align256((int64_t)s->n * 8);                 // dinv
+  sz[4] = align256(sumf * max_rhs * 8);                // wbuf
+  sz[5] = align256((int64_t)s->n * max_rhs * 8);       // xperm
+  sz[6] = 256;                                         // amax
+  sz[7] = 256;                                         // info
+}
+
+extern "C" int64_t eigd_factor_workspace_bytes(eigd_symbolic* s, int max_rhs) {
+  if (build_symdev(s)) return -1;
+  int64_t sz[8], tot = 0;
+  factor_layout(s, ((SymDevHolder*)s->dev)->linv_total, std::max(1, max_rhs), sz);
+  for (int i = 0; i < 8; ++i) tot += sz[i];
+  return tot + 256;
+}
+
+// d_workspace == NULL: the library allocates (cudaMalloc) and owns the arrays; otherwise they are carved
+// out of the caller's buffer (a torch tensor: the caching allocator then recycles it between factors)
+extern "C" int eigd_factor_create_in(eigd_symbolic* s, int max_rhs, void* d_workspace, int64_t workspace_bytes,
+                                     eigd_factor** out) {
   int rc = build_symdev(s);
   if (rc) return rc;
   auto* f = new eigd_factor();
   f->sym = s;
   f->h = (SymDevHolder*)s->dev;
   f->max_rhs = std::max(1, max_rhs);
-  int64_t nfront = s->front_off[s->nsuper], sumf = s->w_off[s->nsuper];
-  auto alloc = [&](void** p, int64_t bytes) -> int {
-    EIGD_CUDA(cudaMalloc(p, (size_t)std::max<int64_t>(bytes, 8)));
-    f->bytes += bytes;
-    return 0;
-  };
-  rc |= alloc((void**)&f->fronts, nfront * 8);
-  rc |= alloc((void**)&f->linv, f->h->linv_total * 8);
-  rc |= alloc((void**)&f->dval, (int64_t)s->n * 8);
-  rc |= alloc((void**)&f->dinv, (int64_t)s->n * 8);
-  rc |= alloc((void**)&f->wbuf, sumf * f->max_rhs * 8);
-  rc |= alloc((void**)&f->xperm, (int64_t)s->n * f->max_rhs * 8);
-  rc |= alloc((void**)&f->amax, 8);
-  rc |= alloc((void**)&f->info, 32);
-  if (rc) { eigd_factor_destroy(f); return rc; }
+  int64_t sz[8], tot = 0;
+  factor_layout(s, f->h->linv_total, f->max_rhs, sz);
+  for (int i = 0; i < 8; ++i) tot += sz[i];
+  char* base = nullptr;
+  if (d_workspace) {
+    base = (char*)(((uintptr_t)d_workspace + 255) / 256 * 256);
+    if ((base - (char*)d_workspace) + tot > workspace_bytes) {
+      eigd_set_error("factor_create_in: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)(tot + 256));
+      delete f;
+      return 3;
+    }
+    f->owns = false;
+  } else {
+    cudaError_t e = cudaMalloc((void**)&base, (size_t)tot);
+    if (e != cudaSuccess) { eigd_set_error("factor_create: cudaMalloc(%lld) -> %s", (long long)tot, cudaGetErrorString(e)); delete f; return 100 + (int)e; }
+    f->owns = true;
+  }
+  f->base = base;
+  f->bytes = tot;
+  char* p = base;
+  f->fronts = (double*)p; p += sz[0];
+  f->linv = (double*)p; p += sz[1];
+  f->dval = (double*)p; p += sz[2];
+  f->dinv = (double*)p; p += sz[3];
+  f->wbuf = (double*)p; p += sz[4];
+  f->xperm = (double*)p; p += sz[5];
+  f->amax = (unsigned long long*)p; p += sz[6];
+  f->info = (unsigned long long*)p;
   *out = f;
   return 0;
 }
 
+extern "C" int eigd_factor_create(eigd_symbolic* s, int max_rhs, eigd_factor** out) {
+  return eigd_factor_create_in(s, max_rhs, nullptr, 0, out);
+}
+
 extern "C" void eigd_factor_destroy(eigd_factor* f) {
   if (!f) return;
-  cudaFree(f->fronts); cudaFree(f->linv); cudaFree(f->dval); cudaFree(f->dinv);
-  cudaFree(f->wbuf); cudaFree(f->xperm); cudaFree(f->amax); cudaFree(f->info);
+  if (f->owns && f->base) cudaFree(f->base);
   delete f;
 }
 

@@ -33,6 +33,44 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
 
+class Timeline:
+    """Optional per-call CUDA-event timing of the heavy entry points (used by bench.py for the live
+    roofline numbers).  Events are recorded on the stream the kernels are launched on (torch's
+    current stream, see ``init``) and only resolved in ``summary`` after a synchronize."""
+    enabled = False
+    records = {}
+
+    @classmethod
+    def begin(cls, cat):
+        if not cls.enabled:
+            return None
+        e0 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        return (cat, e0)
+
+    @classmethod
+    def end(cls, tok, nbytes=0, launches=0):
+        if tok is None:
+            return
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        cls.records.setdefault(tok[0], []).append((tok[1], e1, nbytes, launches))
+
+    @classmethod
+    def reset(cls):
+        cls.records = {}
+
+    @classmethod
+    def summary(cls):
+        torch.cuda.synchronize()
+        out = {}
+        for cat, recs in cls.records.items():
+            ms = sum(a.elapsed_time(b) for a, b, _, _ in recs)
+            out[cat] = {"calls": len(recs), "ms": ms, "bytes": float(sum(r[2] for r in recs)),
+                        "launches": int(sum(r[3] for r in recs))}
+        return out
+
+
 def init(device=None):
     """Select the CUDA device and allocate the reduction workspace."""
     lib = _lib.load()
@@ -134,9 +172,12 @@ class CsrDevice:
             out = empty(n, k) if X.dim() == 2 else empty(n)
             beta = 0.0
         Y2 = _as2d(_chk(out, "out"))
+        tok = Timeline.begin("spmm")
         check(_lib.load().eigd_csr_spmm(n, _ptr(self.indptr), _ptr(self.indices), _ptr(self.data),
                                         _ptr(X2), X2.stride(0), X2.stride(1), _ptr(Y2), Y2.stride(0), Y2.stride(1),
                                         k, float(alpha), float(beta)), "csr_spmm")
+        # algorithmic bytes: nnz*12 + (n+1)*4 + 2*n*k*8
+        Timeline.end(tok, self.nnz * 12 + (n + 1) * 4 + 2 * n * k * 8, 1)
         return out
 
     def __matmul__(self, X):
@@ -321,7 +362,14 @@ class Factor:
         self.sym = symbolic
         self.n = symbolic.n
         h = ctypes.c_void_p()
-        check(_lib.load().eigd_factor_create(symbolic.handle, int(max_rhs), ctypes.byref(h)), "factor_create")
+        lib = _lib.load()
+        nbytes = int(lib.eigd_factor_workspace_bytes(symbolic.handle, int(max_rhs)))
+        if nbytes < 0:
+            check(1, "factor_workspace_bytes")
+        # torch owns the memory: the caching allocator recycles it when this factor is dropped
+        self._workspace = torch.empty(nbytes, dtype=torch.uint8, device=dev())
+        check(lib.eigd_factor_create_in(symbolic.handle, int(max_rhs), _ptr(self._workspace), nbytes, ctypes.byref(h)),
+              "factor_create_in")
         self.handle = h
         self.max_rhs = int(max_rhs)
 
@@ -334,8 +382,19 @@ class Factor:
             pass
 
     def numeric(self, d_vals, d_map):
+        tok = Timeline.begin("factor")
+        l0 = launch_count()
         check(_lib.load().eigd_factor_numeric(self.handle, d_vals.numel(), _ptr(_chk(d_vals)), _ptr(d_map)), "factor_numeric")
+        Timeline.end(tok, 0, launch_count() - l0)
         return self
+
+    def solve_bytes(self, k):
+        """Algorithmic bytes of one forward+backward sweep with k right-hand sides:
+        2*(nnz(L)*8 + idx(L)) + n*8 + 4*n*k*8, idx(L) = the supernodal row lists (int32)."""
+        if not hasattr(self, "_sb"):
+            self._sb = (self.sym.query("nnzL"), self.sym.query("sum_front") - self.n)
+        nnzL, nidx = self._sb
+        return 2 * (nnzL * 8 + nidx * 4) + self.n * 8 + 4 * self.n * k * 8
 
     def info(self):
         out = (ctypes.c_int64 * 3)()
@@ -353,8 +412,12 @@ class Factor:
         if out is None:
             out = torch.empty_like(B)
         X2 = _as2d(_chk(out, "out"))
+        tok = Timeline.begin("solve")
+        l0 = launch_count() if tok else 0
         check(_lib.load().eigd_factor_solve(self.handle, _ptr(B2), B2.stride(0), B2.stride(1), _ptr(X2), X2.stride(0),
                                             X2.stride(1), B2.shape[1]), "factor_solve")
+        if tok:
+            Timeline.end(tok, self.solve_bytes(B2.shape[1]), launch_count() - l0)
         return out
 
 

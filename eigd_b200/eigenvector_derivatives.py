@@ -22,7 +22,7 @@ import numpy as np
 import torch
 
 from . import device as D
-from ._hostdev import as_csr_device, is_dev, like_input, small_to_dev, to_dev, to_host
+from ._hostdev import XFER, as_csr_device, is_dev, like_input, small_to_dev, to_dev, to_host
 from .arpack import eigsh_mod
 
 __all__ = ["SpLuOperator", "add_eig_total_derivative", "eval_adjoint_residual_norm", "are_eigenvalues_repeated",
@@ -70,6 +70,7 @@ class SpLuOperator:
             indptr_h = np.ascontiguousarray(mat.indptr, dtype=np.int32)
             indices_h = np.ascontiguousarray(mat.indices, dtype=np.int32)
             csr = D.CsrDevice(indptr_h, indices_h, mat.data, mat.shape)
+            XFER["h2d"] += mat.nnz * 12 + (mat.shape[0] + 1) * 4
         if csr.shape[0] != csr.shape[1]:
             raise ValueError("expected square matrix")
         self.shape = csr.shape
@@ -389,13 +390,17 @@ def _basis_dev(V):
     return to_dev(np.ascontiguousarray(np.asarray(V).T)).T
 
 
-def _laa_dev(Phib_d, Bd, factor, sigma, lam, V_d, Y, theta, indices, b_ortho, mode):
+def _laa_dev(Phib_d, Bd, factor, sigma, lam, V_d, Y, theta, indices, b_ortho, mode, cols=None, Nfull=None):
+    """``cols`` / ``Nfull``: Phib_d and lam hold only the modes ``cols`` out of ``Nfull`` (mode sharding)."""
     m, N = len(theta), Phib_d.shape[1]
     Yb = to_host(D.gemm_tn(V_d, Phib_d))                      # (m, N) = V^T Phib   (:502)
     Dm = np.zeros((m, N))
-    first = indices[:N]
+    Nfull = N if Nfull is None else Nfull
+    first = indices[:Nfull] if cols is None else indices[np.asarray(cols)]
+    if cols is not None and not b_ortho:
+        raise NotImplementedError("column subsets are only used with b_ortho=True")
     if b_ortho:
-        rest = indices[N:]
+        rest = indices[Nfull:]
         Dm[rest, :] = (Y[:, rest].T @ Yb) / (theta[first][None, :] - theta[rest][:, None])   # (:503-508)
     else:
         for j in range(N):
@@ -581,11 +586,12 @@ def _masked_inverse(vals, active):
     return out
 
 
-def _sibk_dev(Phib_d, Ad, Bd, lam, Phi_d, mode, psi_d, sigma, factor, rtol, atol, maxiter):
+def _sibk_dev(Phib_d, Ad, Bd, lam, Phi_d, mode, psi_d, sigma, factor, rtol, atol, maxiter, rnorm0=None):
     n, N = Phib_d.shape
     lam = np.asarray(lam, dtype=float)
     lam_d = small_to_dev(lam)
-    rnorm0 = float(np.sqrt(np.max(to_host(D.col_dot(Phib_d, Phib_d)))))          # :1170
+    if rnorm0 is None:                                                           # :1170 (max over ALL modes)
+        rnorm0 = float(np.sqrt(np.max(to_host(D.col_dot(Phib_d, Phib_d)))))
     BPhi = Bd.spmm(Phi_d)                                                        # :1173
     G = -to_host(D.gemm_tn(Phi_d, Phib_d))                                       # :1180
     R = _neg_sum(_contig(Phib_d), _apply_L(Ad, Bd, lam_d, psi_d, mode))          # :1189-1193
@@ -666,11 +672,12 @@ def sibk(Phib, A, B, lam, Phi, mode="normal", psi=None, sigma=None, factor=None,
     return _return_psi(psi_d, psi, Phib), data, info
 
 
-def _pcpg_dev(Phib_d, Ad, Bd, lam, Phi_d, mode, psi_d, factor, rtol, atol, maxiter, reset):
+def _pcpg_dev(Phib_d, Ad, Bd, lam, Phi_d, mode, psi_d, factor, rtol, atol, maxiter, reset, rnorm0=None):
     n, N = Phib_d.shape
     lam = np.asarray(lam, dtype=float)
     lam_d = small_to_dev(lam)
-    rnorm0 = float(np.sqrt(np.max(to_host(D.col_dot(Phib_d, Phib_d)))))
+    if rnorm0 is None:
+        rnorm0 = float(np.sqrt(np.max(to_host(D.col_dot(Phib_d, Phib_d)))))
     BPhi = Bd.spmm(Phi_d)
     R = _neg_sum(_contig(Phib_d), _apply_L(Ad, Bd, lam_d, psi_d, mode))           # :806
     # G[:, i] = Phi^T R_i ; R_i -= BPhi G[:, i]   (:807-811)
@@ -725,11 +732,12 @@ def pcpg(Phib, A, B, lam, Phi, mode="normal", psi=None, sigma=None, factor=None,
     return _return_psi(psi_d, psi, Phib), data, info
 
 
-def _pgmres_dev(Phib_d, Ad, Bd, lam, Phi_d, mode, psi_d, factor, rtol, atol, maxiter):
+def _pgmres_dev(Phib_d, Ad, Bd, lam, Phi_d, mode, psi_d, factor, rtol, atol, maxiter, rnorm0=None):
     n, N = Phib_d.shape
     lam = np.asarray(lam, dtype=float)
     lam_d = small_to_dev(lam)
-    rnorm0 = float(np.sqrt(np.max(to_host(D.col_dot(Phib_d, Phib_d)))))
+    if rnorm0 is None:
+        rnorm0 = float(np.sqrt(np.max(to_host(D.col_dot(Phib_d, Phib_d)))))
     BPhi = Bd.spmm(Phi_d)
     R = _neg_sum(_contig(Phib_d), _apply_L(Ad, Bd, lam_d, psi_d, mode))           # :985
     Gd = D.gemm_tn(Phi_d, R)
@@ -817,6 +825,16 @@ class _SolverBase:
             raise TypeError("factor must be an eigd_b200.SpLuOperator (device LDL^T); there is no CPU fallback")
         return n
 
+    def _publish_phi(self, Phi_d, A):
+        """numpy callers get a host copy of the eigenvectors (reference convention); callers that handed
+        in device matrices keep them in HBM."""
+        if isinstance(A, D.CsrDevice):
+            self.Phi = Phi_d
+            self._Phi_host_sig = None
+        else:
+            self.Phi = to_host(Phi_d)
+            self._Phi_host_sig = self._signature(self.Phi)
+
     def _phi_dev(self):
         """Device copy of the eigenvectors; the host array is authoritative if the caller has
         modified it since solve() (the examples flip signs in place, natural_frequency.py:383-390)."""
@@ -849,36 +867,62 @@ class _SolverBase:
         Phi_d = self._phi_dev()
         lam = np.asarray(lam, dtype=float)
         callback = kwargs.pop("callback", None)
-        if lanczos_guess or method == "laa":
-            psi_d = _laa_dev(Phib_d, self._Bd, self.factor, self.sigma, lam, self._V_d, self.Y, self.theta, self.indices,
-                             True, self.mode)
+        N = self.N
+        shard = getattr(self, "sharding", None)
+        if shard is not None and (shard.world == 1 or method == "dl"):
+            shard = None                      # dl is one sequential sweep over the Lanczos vectors: replicated
+        if shard is None:
+            cols, Phib_s, lam_s = None, Phib_d, lam
+        else:                                 # per-mode shard: this rank owns modes rank, rank+world, ...
+            cols = shard.my_cols(N)
+            lam_s = lam[cols]
+            Phib_s = D.empty(n, len(cols))
+            if len(cols):
+                D.copy2d(Phib_d[:, shard.rank::shard.world], Phib_s)
+        Ns = Phib_s.shape[1]
+        if (lanczos_guess or method == "laa") and Ns:
+            psi_s = _laa_dev(Phib_s, self._Bd, self.factor, self.sigma, lam_s, self._V_d, self.Y, self.theta,
+                             self.indices, True, self.mode, cols=cols, Nfull=N)
         else:
-            psi_d = D.zeros(n, self.N)
-        data = {}
-        if method == "laa":
-            G = -to_host(D.gemm_tn(Phi_d, Phib_d))
-            data = _apply_correction_dev(lam, Phi_d, psi_d, G, self.eig_atol, self.mode)
-        elif method == "dl":
+            psi_s = D.zeros(n, Ns)
+        if method == "dl":
             psi_d, data = _dl_dev(Phib_d, self._Bd, self.factor, self.sigma, lam, Phi_d, self.indices, self._V_d,
                                   self.T, self.Y, self.theta, self.eig_atol, self.mode)
-        else:
+            return like_input(psi_d, Phib), data
+        G, info, hist = None, [], []
+        rn0 = None if shard is None else float(np.sqrt(np.max(to_host(D.col_dot(Phib_d, Phib_d)))))
+        if method != "laa" and Ns:
             if method == "sibk":
                 if kwargs.pop("bs_target", 1) != 1 or kwargs.pop("update_guess", False):
                     raise NotImplementedError("sibk on the device path supports bs_target=1, update_guess=False")
                 kwargs.pop("nrestart", None)
-                G, info, hist = _sibk_dev(Phib_d, self._Ad, self._Bd, lam, Phi_d, self.mode, psi_d, float(self.sigma),
-                                          self.factor, rtol, atol, kwargs.pop("maxiter", 50))
+                G, info, hist = _sibk_dev(Phib_s, self._Ad, self._Bd, lam_s, Phi_d, self.mode, psi_s, float(self.sigma),
+                                          self.factor, rtol, atol, kwargs.pop("maxiter", 50), rnorm0=rn0)
             elif method == "pcpg":
-                G, info, hist = _pcpg_dev(Phib_d, self._Ad, self._Bd, lam, Phi_d, self.mode, psi_d, self.factor, rtol, atol,
-                                          kwargs.pop("maxiter", 100), kwargs.pop("reset", 25))
+                G, info, hist = _pcpg_dev(Phib_s, self._Ad, self._Bd, lam_s, Phi_d, self.mode, psi_s, self.factor, rtol,
+                                          atol, kwargs.pop("maxiter", 100), kwargs.pop("reset", 25), rnorm0=rn0)
             else:
-                G, info, hist = _pgmres_dev(Phib_d, self._Ad, self._Bd, lam, Phi_d, self.mode, psi_d, self.factor, rtol,
-                                            atol, kwargs.pop("maxiter", 50))
+                G, info, hist = _pgmres_dev(Phib_s, self._Ad, self._Bd, lam_s, Phi_d, self.mode, psi_s, self.factor,
+                                            rtol, atol, kwargs.pop("maxiter", 50), rnorm0=rn0)
             if kwargs:
                 raise TypeError("unexpected keyword arguments %r" % sorted(kwargs))
-            self.adjoint_info = info
-            _replay(callback, hist)
-            data = _apply_correction_dev(lam, Phi_d, psi_d, G, self.eig_atol, self.mode)
+        if shard is None:
+            psi_d = psi_s
+        else:                                 # the two gathers of the sharded adjoint (dist.py)
+            psi_d = shard.allgather_cols(psi_s, N, transpose=D.copy2d)
+            if method != "laa":
+                parts = shard.allgather_object((G if G is not None else np.zeros((N, 0)), info, hist))
+                G = shard.merge_cols_host([p[0] for p in parts], N)
+                info_all, hist_all = [0] * N, [[] for _ in range(N)]
+                for r, p in enumerate(parts):
+                    for c, i in enumerate(shard.my_cols(N, r)):
+                        info_all[i], hist_all[i] = p[1][c], p[2][c]
+                info, hist = info_all, hist_all
+        if method == "laa":
+            G = -to_host(D.gemm_tn(Phi_d, Phib_d))
+        self.adjoint_info = info
+        _replay(callback, hist)
+        data = _apply_correction_dev(lam, Phi_d, psi_d, G, self.eig_atol, self.mode)
         return like_input(psi_d, Phib), data
 
 
@@ -971,9 +1015,8 @@ class BasicLanczos(_SolverBase):
         Phi_d = D.empty(n, self.N)
         D.gemm_nn(self._V_d, small_to_dev(self.Y0), Phi_d, alpha=1.0, beta=0.0)            # :1648
         self._Phi_d = Phi_d
-        self.Phi = to_host(Phi_d)
-        self._Phi_host_sig = self._signature(self.Phi)
         self._V_host = None
+        self._publish_phi(Phi_d, A)
         return self.lam0, self.Phi
 
     @property
@@ -1040,8 +1083,7 @@ class IRAM(_SolverBase):
             if mac[i] < 0.0:
                 self.Y[:, self.indices[i]] *= -1.0
         self._Phi_d = st.Z
-        self.Phi = to_host(st.Z)
-        self._Phi_host_sig = self._signature(self.Phi)
+        self._publish_phi(st.Z, A)
         return self.lam, self.Phi
 
     @property

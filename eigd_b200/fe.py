@@ -154,6 +154,7 @@ class Q4Problem:
         self.ks_d, self.ms_d = D.empty(self.nelems), D.empty(self.nelems)
         self.dk_d, self.dm_d = D.empty(self.nelems), D.empty(self.nelems)
         self._par_c = (ctypes.c_double * 4)(*[float(v) for v in self.par])
+        self.sharding = None          # dist.ModeSharding: element-range shards of the df/dx reduction
         self.dAdx, self.dBdx = _Half(self, "A"), _Half(self, "B")
         self.dAdx.fused_with, self.dBdx.fused_with = self.dBdx, self.dAdx
 
@@ -197,10 +198,18 @@ class Q4Problem:
         V2 = V2 if V2.is_contiguous() else V2.contiguous()
         WA2 = None if WA2 is None else (WA2 if WA2.is_contiguous() else WA2.contiguous())
         WB2 = None if WB2 is None else (WB2 if WB2.is_contiguous() else WB2.contiguous())
-        out = D.zeros(self.nelems)
-        D.q4_quadforms(self.kid, self.conn_d, self.xy_d, self.cmat6_d, WA2, WB2, V2, self.dk_d, self.dm_d,
-                       float(cA), -float(cB), out)
-        return out
+        shard = self.sharding
+        if shard is None or shard.world == 1:
+            out = D.zeros(self.nelems)
+            D.q4_quadforms(self.kid, self.conn_d, self.xy_d, self.cmat6_d, WA2, WB2, V2, self.dk_d, self.dm_d,
+                           float(cA), -float(cB), out)
+            return out
+        lo, hi = shard.my_range(self.nelems)                  # element-range shard + one all-gather (dist.py)
+        part = D.zeros(hi - lo)
+        if hi > lo:
+            D.q4_quadforms(self.kid, self.conn_d[lo:hi], self.xy_d, self.cmat6_d, WA2, WB2, V2, self.dk_d[lo:hi],
+                           self.dm_d[lo:hi], float(cA), -float(cB), part)
+        return shard.allgather_ranges(part, self.nelems)
 
     def scatter_to_nodes(self, evals, scale=0.25):
         """rho_b[v] = scale * sum_{e ni v} evals[e] (examples/thermal.py:612-615)."""

@@ -94,6 +94,10 @@ int eigd_symbolic_assembly_map_host(const eigd_symbolic* s, int n, const int* in
 int eigd_symbolic_assembly_map_device(eigd_symbolic* s, int n, const int* d_indptr, const int* d_indices, int64_t* d_map);
 
 int eigd_factor_create(eigd_symbolic* s, int max_rhs, eigd_factor** out);
+/* same, with every device array carved out of a caller-owned buffer of eigd_factor_workspace_bytes()
+ * bytes (a torch tensor, so that the caching allocator recycles it: no cudaMalloc / cudaFree per design) */
+int64_t eigd_factor_workspace_bytes(eigd_symbolic* s, int max_rhs);
+int eigd_factor_create_in(eigd_symbolic* s, int max_rhs, void* d_workspace, int64_t workspace_bytes, eigd_factor** out);
 void eigd_factor_destroy(eigd_factor* f);
 /* numeric factorisation from device CSR values + device assembly map */
 int eigd_factor_numeric(eigd_factor* f, int64_t nnz, const double* d_vals, const int64_t* d_map);

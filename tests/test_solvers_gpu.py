@@ -233,7 +233,8 @@ def test_device_resident_path_matches_host_path(E, th):
     s.seed = 2
     lam, Phi = s.solve(Ad, Bd, f, sigma)
     assert np.abs(lam - th["lam"]).max() < 1e-10 * np.abs(th["lam"]).max()
-    _, sgn = align_signs(Phi, th["Phi"])
+    assert isinstance(Phi, torch.Tensor) and Phi.is_cuda          # device matrices in -> eigenvectors stay in HBM
+    _, sgn = align_signs(Phi.cpu().numpy(), th["Phi"])
     Phib_d = torch.as_tensor(th["Phib"] * sgn, device="cuda")
     psi_d, data = s.solve_adjoint(Phib_d, method="sibk", rtol=1e-12)
     assert isinstance(psi_d, torch.Tensor)
