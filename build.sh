@@ -8,12 +8,14 @@ mkdir -p build
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -O3 ${EIGD_NVCC_EXTRA}"
 pids=()
-for f in dense sparse factor fe; do
+for f in dense sparse factor solve fe; do
   $NVCC $FLAGS -c $SRC/$f.cu -o build/$f.o &
   pids+=($!)
 done
-g++ -O3 -std=c++17 -fPIC -c $SRC/symbolic.cpp -o build/symbolic.o &
-pids+=($!)
-for p in "${pids[@]}"; do wait $p; done
-$NVCC -shared -o $OUT build/dense.o build/sparse.o build/factor.o build/fe.o build/symbolic.o -lcudart
+for f in symbolic solve_plan; do
+  g++ -O3 -std=c++17 -fPIC -c $SRC/$f.cpp -o build/$f.o &
+  pids+=($!)
+done
+for p in "${pids[@]}"; do wait $p || exit 1; done
+$NVCC -shared -o $OUT build/dense.o build/sparse.o build/factor.o build/solve.o build/fe.o build/symbolic.o build/solve_plan.o -lcudart
 echo "built $OUT"

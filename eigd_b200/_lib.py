@@ -36,6 +36,7 @@ SIGNATURES = {
     "eigd_symbolic_get": (c_i64, [c_ptr, c_int, c_ptr, c_i64]),
     "eigd_symbolic_assembly_map_host": (c_int, [c_ptr, c_int, c_ptr, c_ptr, c_ptr]),
     "eigd_symbolic_assembly_map_device": (c_int, [c_ptr, c_int, c_ptr, c_ptr, c_ptr]),
+    "eigd_solve_plan_get": (c_i64, [c_ptr, c_int, c_int, c_ptr, c_i64]),
     "eigd_factor_create": (c_int, [c_ptr, c_int, c_ptr]),
     "eigd_factor_workspace_bytes": (c_i64, [c_ptr, c_int]),
     "eigd_factor_create_in": (c_int, [c_ptr, c_int, c_ptr, c_i64, c_ptr]),

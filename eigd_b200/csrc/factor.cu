@@ -7,15 +7,16 @@
 //   fronts : one dense column-major f x f block per supernode (lower triangle used);
 //            columns [0, ncols) hold L (unit diagonal implied, D on the diagonal), the
 //            trailing (f-ncols)^2 block is the contribution passed to the parent.
-//   linv   : explicit inverses of the 32x32 unit-lower diagonal blocks of every L11, so the
-//            triangular solves inside a front become small dense products.
-//   wbuf   : per-front work vectors (f x k, row-major) used by the solve; the part below the
-//            pivot rows carries the front's update to its parent (multifrontal solve: no
-//            atomics, deterministic sums).
+//   linv   : explicit inverses of the 32x32 unit-lower diagonal blocks of every L11 (used by the
+//            panel solves of the factorisation).
+//   xinv   : the full inverse X = L11^{-1} of every pivot block (recursive doubling from the
+//            32x32 inverses: X21 = -B^{-1} C A^{-1}).
+//   sfwd / sbwd : the solve panels S = [X ; -L21 X] (f x nc, column-major) and S^T (nc x f):
+//            with them both triangular sweeps of a front are plain dense products with no
+//            dependency inside the front (solve.cu), one grid barrier per tree level.
 // Execution: supernodes are grouped by height in the assembly tree; every level is a handful
 // of batched launches driven by host-built task lists (front, tile).
-#include "common.cuh"
-#include "symbolic.hpp"
+#include "factor_internal.cuh"
 #include "../../include/eigd_b200.h"
 
 #include <algorithm>
@@ -23,42 +24,6 @@
 #include <vector>
 
 namespace {
-
-constexpr int NB = 32;        // pivot block width
-constexpr int TRSM_ROWS = 128;
-constexpr int UPD_TILE = 64;
-constexpr int EA_TILE = 32;
-constexpr int FWD_ROWS = 128;
-constexpr int BWD_COLS = 8;
-
-struct SymDev {
-  int n, nsuper;
-  int *perm, *iperm, *col2sn;
-  int* sn_first;
-  int64_t* sn_rowptr;
-  int* sn_rows;
-  int* rel;
-  int64_t* front_off;
-  int64_t* w_off;
-  int64_t* linv_off;
-  int* sn_parent;
-  int *child_ptr, *child_idx;
-};
-
-struct Launch {
-  int kind;      // 0 extend-add, 1 diag, 2 trsm, 3 update | solve: 4 fwd_diag, 5 fwd_update, 6 bwd_update, 7 bwd_diag
-  int kb;        // pivot block index (factor kinds)
-  int64_t off;   // offset into the task array (int2 entries)
-  int count;
-};
-
-struct SymDevHolder {
-  SymDev d;
-  std::vector<void*> allocs;
-  int2* tasks = nullptr;
-  std::vector<Launch> factor_plan, fwd_plan, bwd_plan;
-  int64_t linv_total = 0;
-};
 
 template <class T>
 int upload(SymDevHolder* h, const std::vector<T>& v, T** out) {
@@ -71,8 +36,11 @@ int upload(SymDevHolder* h, const std::vector<T>& v, T** out) {
   return 0;
 }
 
-void free_symdev(void* p) {
+}  // namespace
+
+static void free_symdev(void* p) {
   auto* h = (SymDevHolder*)p;
+  free_solve_plan_dev(h);
   for (void* a : h->allocs) cudaFree(a);
   if (h->tasks) cudaFree(h->tasks);
   delete h;
@@ -94,6 +62,14 @@ int build_symdev(eigd_symbolic* S) {
   std::vector<int64_t> linv_off(ns + 1, 0);
   for (int k = 0; k < ns; ++k) linv_off[k + 1] = linv_off[k] + (int64_t)((sn_ncols(S, k) + NB - 1) / NB) * NB * NB;
   h->linv_total = linv_off[ns];
+  std::vector<int64_t> soff(ns + 1, 0), xoff(ns + 1, 0);
+  for (int k = 0; k < ns; ++k) {
+    soff[k + 1] = soff[k] + (int64_t)sn_fsize(S, k) * sn_ncols(S, k);
+    xoff[k + 1] = xoff[k] + (int64_t)sn_ncols(S, k) * sn_ncols(S, k);
+  }
+  h->panel_total = soff[ns];
+  h->xinv_total = xoff[ns];
+  if (S->maxcols > 512) { eigd_set_error("build_symdev: supernodes wider than 512 columns are not supported"); return 4; }
   int rc = 0;
   rc |= upload(h, S->perm, &h->d.perm);
   rc |= upload(h, S->iperm, &h->d.iperm);
@@ -105,6 +81,8 @@ int build_symdev(eigd_symbolic* S) {
   rc |= upload(h, S->front_off, &h->d.front_off);
   rc |= upload(h, S->w_off, &h->d.w_off);
   rc |= upload(h, linv_off, &h->d.linv_off);
+  rc |= upload(h, soff, &h->d.soff);
+  rc |= upload(h, xoff, &h->d.xoff);
   rc |= upload(h, S->sn_parent, &h->d.sn_parent);
   rc |= upload(h, S->child_ptr, &h->d.child_ptr);
   rc |= upload(h, S->child_idx, &h->d.child_idx);
@@ -163,34 +141,37 @@ int build_symdev(eigd_symbolic* S) {
       }
       push_launch(h->factor_plan, 3, kb, off);
     }
-    // forward solve
-    int64_t off = (int64_t)tasks.size();
-    for (int i = 0; i < cnt; ++i) tasks.push_back(make_int2(sn[i], 0));
-    push_launch(h->fwd_plan, 4, 0, off);
-    off = (int64_t)tasks.size();
-    for (int i = 0; i < cnt; ++i) {
-      int nt = (sn_nbelow(S, sn[i]) + FWD_ROWS - 1) / FWD_ROWS;
-      for (int t = 0; t < nt; ++t) tasks.push_back(make_int2(sn[i], t));
-    }
-    push_launch(h->fwd_plan, 5, 0, off);
   }
-  for (int l = S->nlevels - 1; l >= 0; --l) {
-    const int* sn = S->level_sn.data() + S->level_ptr[l];
-    int cnt = S->level_ptr[l + 1] - S->level_ptr[l];
+  // ---- after the last level: full inverses of the pivot blocks and the solve panels (all fronts at once)
+  {
     int64_t off = (int64_t)tasks.size();
-    for (int i = 0; i < cnt; ++i) {
-      int nt = (sn_ncols(S, sn[i]) + BWD_COLS - 1) / BWD_COLS;
-      for (int t = 0; t < nt; ++t) tasks.push_back(make_int2(sn[i], t));
+    for (int k = 0; k < ns; ++k) tasks.push_back(make_int2(k, 0));
+    push_launch(h->factor_plan, 4, 0, off);
+    for (int stage = 0, hb = NB; hb < S->maxcols; ++stage, hb *= 2) {
+      off = (int64_t)tasks.size();
+      for (int k = 0; k < ns; ++k) {
+        int nc = sn_ncols(S, k);
+        for (int q = 0; (2 * q + 1) * hb < nc; ++q) {
+          int hh = std::min(hb, nc - (2 * q + 1) * hb);
+          for (int ti = 0; ti * NB < hh; ++ti)
+            for (int tj = 0; tj * NB < hb; ++tj) tasks.push_back(make_int2(k, q * 64 + ti * 8 + tj));
+        }
+      }
+      int64_t end = (int64_t)tasks.size();
+      push_launch(h->factor_plan, 5, stage, off);       // T = C A^-1
+      if (end > off) h->factor_plan.push_back({6, stage, off, (int)(end - off)});   // X21 = -B^-1 T (same tasks)
     }
-    push_launch(h->bwd_plan, 6, 0, off);
     off = (int64_t)tasks.size();
-    for (int i = 0; i < cnt; ++i) tasks.push_back(make_int2(sn[i], 0));
-    push_launch(h->bwd_plan, 7, 0, off);
+    for (int k = 0; k < ns; ++k)
+      for (int t = 0; t * NB < sn_fsize(S, k); ++t) tasks.push_back(make_int2(k, t));
+    push_launch(h->factor_plan, 7, 0, off);
   }
   EIGD_CUDA(cudaMalloc((void**)&h->tasks, std::max<size_t>(tasks.size(), 1) * sizeof(int2)));
   EIGD_CUDA(cudaMemcpy(h->tasks, tasks.data(), tasks.size() * sizeof(int2), cudaMemcpyHostToDevice));
-  return 0;
+  return build_solve_plan_dev(S, h);
 }
+
+namespace {
 
 // ---------------------------------------------------------------------------------------
 // integer kernel: CSR non-zero -> slot in front storage (bit-exact twin of the host routine)
@@ -338,7 +319,7 @@ diag_factor_kernel(SymDev d, const int2* __restrict__ tasks, int kb, double* __r
     if (i >= j) F[(j0 + i) + (int64_t)(j0 + j) * f] = T[i][j];
   }
   double* Lo = linv + d.linv_off[s] + (int64_t)kb * NB * NB;
-  for (int e = tid; e < NB * NB; e += blockDim.x) Lo[e] = Li[e / NB][e % NB];
+  for (int e = tid; e < NB * NB; e += blockDim.x) Lo[e] = Li[e % NB][e / NB];   // column-major: Lo[i + j*NB]
   if (tid < bs) {
     dval[first + j0 + tid] = T[tid][tid];
     dinv[first + j0 + tid] = 1.0 / T[tid][tid];
@@ -364,7 +345,7 @@ trsm_kernel(SymDev d, const int2* __restrict__ tasks, int kb, double* __restrict
   int j0 = kb * NB;
   int bs = min(NB, nc - j0);
   const double* Lg = linv + d.linv_off[s] + (int64_t)kb * NB * NB;
-  for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) Li[e / NB][e % NB] = Lg[e];
+  for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) Li[e % NB][e / NB] = Lg[e];
   if (threadIdx.x < NB) di[threadIdx.x] = (threadIdx.x < bs) ? dinv[first + j0 + threadIdx.x] : 0.0;
   __syncthreads();
   int64_t i = (int64_t)j0 + bs + (int64_t)tk.y * TRSM_ROWS + threadIdx.x;
@@ -442,206 +423,146 @@ trailing_update_kernel(SymDev d, const int2* __restrict__ tasks, int kb, double*
 }
 
 // ---------------------------------------------------------------------------------------
-// solve kernels (k right-hand sides; work vectors row-major with stride k)
+// solve panels: X = L11^{-1} by recursive doubling, S = [X ; -L21 X] and S^T
 // ---------------------------------------------------------------------------------------
-// forward, pivot rows: gather b, add the children's updates, w1 <- L11^{-1} w1
-__global__ void __launch_bounds__(256)
-fwd_diag_kernel(SymDev d, const int2* __restrict__ tasks, const double* __restrict__ fronts,
-                const double* __restrict__ linv, double* __restrict__ wbuf, const double* __restrict__ B,
-                int64_t brs, int64_t bcs, int k) {
-  extern __shared__ double W1[];  // nc * k
-  __shared__ double tmp[NB * 32];
-  int s = tasks[blockIdx.x].x;
-  int first = d.sn_first[s];
-  int nc = d.sn_first[s + 1] - first;
-  int nb = (int)(d.sn_rowptr[s + 1] - d.sn_rowptr[s]);
-  int64_t f = nc + nb;
-  const double* F = fronts + d.front_off[s];
-  double* w = wbuf + d.w_off[s] * k;
-  const int tid = threadIdx.x;
-  for (int e = tid; e < nc * k; e += blockDim.x) {
-    int i = e / k, r = e - i * k;
-    W1[e] = B[(int64_t)d.perm[first + i] * brs + (int64_t)r * bcs];
-  }
-  for (int64_t e = tid; e < (int64_t)nb * k; e += blockDim.x) w[(int64_t)nc * k + e] = 0.0;
-  __syncthreads();
-  for (int q = d.child_ptr[s]; q < d.child_ptr[s + 1]; ++q) {
-    int c = d.child_idx[q];
-    int ncc = d.sn_first[c + 1] - d.sn_first[c];
-    int nbc = (int)(d.sn_rowptr[c + 1] - d.sn_rowptr[c]);
-    const double* wc = wbuf + (d.w_off[c] + ncc) * k;
-    const int* rel = d.rel + d.sn_rowptr[c];
-    for (int e = tid; e < nbc * k; e += blockDim.x) {
-      int i = e / k, r = e - i * k;
-      int t = rel[i];
-      if (t < nc) W1[t * k + r] += wc[e];
-      else w[(int64_t)t * k + r] += wc[e];
+// 32 x 32 output tile of a product with 256 threads: thread (tx, ty) accumulates the four outputs
+// (tx, ty + 8q).  fa(i, kk) / fb(kk, j) return the operand entries (0 outside their valid range).
+template <class FA, class FB>
+__device__ __forceinline__ void tile_gemm32(int K, FA fa, FB fb, double acc[4], double (*As)[NB + 1], double (*Bs)[NB + 1]) {
+  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) acc[q] = 0.0;
+  for (int k0 = 0; k0 < K; k0 += NB) {
+    for (int e = tid; e < NB * NB; e += 256) {
+      int i = e & 31, kk = e >> 5;
+      As[i][kk] = (k0 + kk < K) ? fa(i, k0 + kk) : 0.0;
+      Bs[i][kk] = (k0 + i < K) ? fb(k0 + i, kk) : 0.0;      // Bs[kk][j] with (kk, j) = (i, kk) of this loop
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int kk = 0; kk < NB; ++kk) {
+      double a = As[tx][kk];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[q] = fma(a, Bs[kk][ty + 8 * q], acc[q]);
     }
     __syncthreads();
   }
-  int nblk = (nc + NB - 1) / NB;
-  for (int kb = 0; kb < nblk; ++kb) {
-    int j0 = kb * NB;
-    int bs = min(NB, nc - j0);
-    const double* Li = linv + d.linv_off[s] + (int64_t)kb * NB * NB;
-    for (int e = tid; e < bs * k; e += blockDim.x) {
-      int i = e / k, r = e - i * k;
-      double sum = 0.0;
-      for (int kk = 0; kk <= i; ++kk) sum = fma(Li[i * NB + kk], W1[(j0 + kk) * k + r], sum);
-      tmp[e] = sum;
-    }
-    __syncthreads();
-    for (int e = tid; e < bs * k; e += blockDim.x) W1[j0 * k + e] = tmp[e];
-    __syncthreads();
-    int rest = nc - j0 - bs;
-    for (int e = tid; e < rest * k; e += blockDim.x) {
-      int i = j0 + bs + e / k, r = e % k;
-      double sum = 0.0;
-      for (int kk = 0; kk < bs; ++kk) sum = fma(F[i + (int64_t)(j0 + kk) * f], W1[(j0 + kk) * k + r], sum);
-      W1[i * k + r] -= sum;
-    }
-    __syncthreads();
-  }
-  for (int e = tid; e < nc * k; e += blockDim.x) w[e] = W1[e];
 }
 
-// forward, rows below the pivots: w2 -= L21 * w1 ; one thread per row
-template <int KT>
-__global__ void __launch_bounds__(FWD_ROWS)
-fwd_update_kernel(SymDev d, const int2* __restrict__ tasks, const double* __restrict__ fronts,
-                  double* __restrict__ wbuf, int k) {
-  extern __shared__ double X1[];  // nc * k
+// X <- diag(linv blocks) (X was zeroed by a memset); one CTA per front
+__global__ void __launch_bounds__(256)
+inverse_init_kernel(SymDev d, const int2* __restrict__ tasks, const double* __restrict__ linv, double* __restrict__ xinv) {
+  int s = tasks[blockIdx.x].x;
+  int nc = d.sn_first[s + 1] - d.sn_first[s];
+  double* X = xinv + d.xoff[s];
+  const double* Lo = linv + d.linv_off[s];
+  int nblk = (nc + NB - 1) / NB;
+  for (int e = threadIdx.x; e < nblk * NB * NB; e += blockDim.x) {
+    int kb = e / (NB * NB), r = e - kb * NB * NB;
+    int i = r & 31, j = r >> 5;
+    int gi = kb * NB + i, gj = kb * NB + j;
+    if (gi < nc && gj < nc && i >= j) X[gi + (int64_t)gj * nc] = Lo[e];
+  }
+}
+
+// doubling stage, first product: T = C A^{-1} for the pair (lo block, hi block) of width hb
+__global__ void __launch_bounds__(256)
+inverse_ca_kernel(SymDev d, const int2* __restrict__ tasks, int hb, const double* __restrict__ fronts,
+                  const double* __restrict__ xinv, double* __restrict__ xtmp) {
+  __shared__ double As[NB][NB + 1];
+  __shared__ double Bs[NB][NB + 1];
+  int2 tk = tasks[blockIdx.x];
+  int s = tk.x, q = tk.y >> 6, ti = (tk.y >> 3) & 7, tj = tk.y & 7;
+  int nc = d.sn_first[s + 1] - d.sn_first[s];
+  int64_t f = nc + (d.sn_rowptr[s + 1] - d.sn_rowptr[s]);
+  int lo0 = 2 * q * hb, hi0 = lo0 + hb, hh = min(hb, nc - hi0);
+  const double* F = fronts + d.front_off[s];
+  const double* X = xinv + d.xoff[s];
+  double* T = xtmp + d.xoff[s];
+  int c0 = lo0 + tj * NB;                 // A^{-1} is lower triangular: terms c >= first column of the tile
+  int K = hb - tj * NB;
+  double acc[4];
+  tile_gemm32(K,
+              [&](int i, int kk) { return (ti * NB + i < hh) ? F[(hi0 + ti * NB + i) + (int64_t)(c0 + kk) * f] : 0.0; },
+              [&](int kk, int j) { return X[(c0 + kk) + (int64_t)(c0 + j) * nc]; }, acc, As, Bs);
+  int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  if (ti * NB + tx < hh)
+#pragma unroll
+    for (int qq = 0; qq < 4; ++qq) T[(hi0 + ti * NB + tx) + (int64_t)(c0 + ty + 8 * qq) * nc] = acc[qq];
+}
+
+// doubling stage, second product: X21 = -B^{-1} T
+__global__ void __launch_bounds__(256)
+inverse_bt_kernel(SymDev d, const int2* __restrict__ tasks, int hb, double* __restrict__ xinv,
+                  const double* __restrict__ xtmp) {
+  __shared__ double As[NB][NB + 1];
+  __shared__ double Bs[NB][NB + 1];
+  int2 tk = tasks[blockIdx.x];
+  int s = tk.x, q = tk.y >> 6, ti = (tk.y >> 3) & 7, tj = tk.y & 7;
+  int nc = d.sn_first[s + 1] - d.sn_first[s];
+  int lo0 = 2 * q * hb, hi0 = lo0 + hb, hh = min(hb, nc - hi0);
+  double* X = xinv + d.xoff[s];
+  const double* T = xtmp + d.xoff[s];
+  int c0 = lo0 + tj * NB;
+  int K = min(hh, (ti + 1) * NB);         // B^{-1} is lower triangular: terms c <= last row of the tile
+  double acc[4];
+  tile_gemm32(K,
+              [&](int i, int kk) { return (ti * NB + i < hh) ? X[(hi0 + ti * NB + i) + (int64_t)(hi0 + kk) * nc] : 0.0; },
+              [&](int kk, int j) { return T[(hi0 + kk) + (int64_t)(c0 + j) * nc]; }, acc, As, Bs);
+  int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  if (ti * NB + tx < hh)
+#pragma unroll
+    for (int qq = 0; qq < 4; ++qq) X[(hi0 + ti * NB + tx) + (int64_t)(c0 + ty + 8 * qq) * nc] = -acc[qq];
+}
+
+// one 32-row tile of the solve panel: S rows < nc are X, rows >= nc are -L21 X; also written transposed
+__global__ void __launch_bounds__(256)
+panel_build_kernel(SymDev d, const int2* __restrict__ tasks, const double* __restrict__ fronts,
+                   const double* __restrict__ xinv, double* __restrict__ sfwd, double* __restrict__ sbwd) {
+  __shared__ double As[NB][NB + 1];
+  __shared__ double Bs[NB][NB + 1];
+  __shared__ double Ts[NB][NB + 1];
   int2 tk = tasks[blockIdx.x];
   int s = tk.x;
   int nc = d.sn_first[s + 1] - d.sn_first[s];
-  int nb = (int)(d.sn_rowptr[s + 1] - d.sn_rowptr[s]);
-  int64_t f = nc + nb;
-  double* w = wbuf + d.w_off[s] * k;
-  for (int e = threadIdx.x; e < nc * k; e += blockDim.x) X1[e] = w[e];
-  __syncthreads();
-  int i = tk.y * FWD_ROWS + threadIdx.x;
-  if (i >= nb) return;
-  const double* Lrow = fronts + d.front_off[s] + nc + i;
-  double acc[KT];
-#pragma unroll
-  for (int r = 0; r < KT; ++r) acc[r] = 0.0;
-#pragma unroll 4
-  for (int j = 0; j < nc; ++j) {
-    double l = Lrow[(int64_t)j * f];
-#pragma unroll
-    for (int r = 0; r < KT; ++r)
-      if (r < k) acc[r] = fma(l, X1[j * k + r], acc[r]);
-  }
-  double* wr = w + (int64_t)(nc + i) * k;
-#pragma unroll
-  for (int r = 0; r < KT; ++r)
-    if (r < k) wr[r] -= acc[r];
-}
-
-// backward, w1 <- D^{-1} w1 - L21^T x(below rows) ; one warp per pivot column
-template <int KT>
-__global__ void __launch_bounds__(BWD_COLS * 32)
-bwd_update_kernel(SymDev d, const int2* __restrict__ tasks, const double* __restrict__ fronts,
-                  double* __restrict__ wbuf, const double* __restrict__ xperm, const double* __restrict__ dinv, int k) {
-  int2 tk = tasks[blockIdx.x];
-  int s = tk.x;
-  int first = d.sn_first[s];
-  int nc = d.sn_first[s + 1] - first;
-  int nb = (int)(d.sn_rowptr[s + 1] - d.sn_rowptr[s]);
-  int64_t f = nc + nb;
-  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int j = tk.y * BWD_COLS + warp;
-  if (j >= nc) return;
-  const double* Lcol = fronts + d.front_off[s] + nc + (int64_t)j * f;
-  const int* rows = d.sn_rows + d.sn_rowptr[s];
-  double acc[KT];
-#pragma unroll
-  for (int r = 0; r < KT; ++r) acc[r] = 0.0;
-  for (int i = lane; i < nb; i += 32) {
-    double l = Lcol[i];
-    const double* xr = xperm + (int64_t)rows[i] * k;
-#pragma unroll
-    for (int r = 0; r < KT; ++r)
-      if (r < k) acc[r] = fma(l, xr[r], acc[r]);
-  }
-#pragma unroll
-  for (int r = 0; r < KT; ++r) acc[r] = warp_sum(acc[r]);
-  if (lane == 0) {
-    double* w = wbuf + (d.w_off[s] + j) * k;
-    double di = dinv[first + j];
-#pragma unroll
-    for (int r = 0; r < KT; ++r)
-      if (r < k) w[r] = w[r] * di - acc[r];
-  }
-}
-
-// backward, pivot rows: x1 <- L11^{-T} w1, scatter to the permuted and the original ordering
-__global__ void __launch_bounds__(256)
-bwd_diag_kernel(SymDev d, const int2* __restrict__ tasks, const double* __restrict__ fronts,
-                const double* __restrict__ linv, const double* __restrict__ wbuf, double* __restrict__ xperm,
-                double* __restrict__ X, int64_t xrs, int64_t xcs, int k) {
-  extern __shared__ double W1[];
-  __shared__ double tmp[NB * 32];
-  int s = tasks[blockIdx.x].x;
-  int first = d.sn_first[s];
-  int nc = d.sn_first[s + 1] - first;
   int64_t f = nc + (d.sn_rowptr[s + 1] - d.sn_rowptr[s]);
+  int r0 = tk.y * NB;
   const double* F = fronts + d.front_off[s];
-  const double* w = wbuf + d.w_off[s] * k;
-  const int tid = threadIdx.x;
-  for (int e = tid; e < nc * k; e += blockDim.x) W1[e] = w[e];
-  __syncthreads();
-  int nblk = (nc + NB - 1) / NB;
-  for (int kb = nblk - 1; kb >= 0; --kb) {
-    int j0 = kb * NB;
-    int bs = min(NB, nc - j0);
-    const double* Li = linv + d.linv_off[s] + (int64_t)kb * NB * NB;
-    for (int e = tid; e < bs * k; e += blockDim.x) {
-      int i = e / k, r = e - i * k;
-      double sum = 0.0;
-      for (int kk = i; kk < bs; ++kk) sum = fma(Li[kk * NB + i], W1[(j0 + kk) * k + r], sum);
-      tmp[e] = sum;
+  const double* X = xinv + d.xoff[s];
+  double* S = sfwd + d.soff[s];
+  double* St = sbwd + d.soff[s];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const bool below = r0 + NB > nc;          // the tile holds rows of L21
+  for (int jb = 0; jb * NB < nc; ++jb) {
+    int c0 = jb * NB;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    if (below)
+      tile_gemm32(nc - c0,
+                  [&](int i, int kk) { int r = r0 + i; return (r >= nc && r < f) ? F[r + (int64_t)(c0 + kk) * f] : 0.0; },
+                  [&](int kk, int j) { return (c0 + j < nc) ? X[(c0 + kk) + (int64_t)(c0 + j) * nc] : 0.0; }, acc, As, Bs);
+    int r = r0 + tx;
+#pragma unroll
+    for (int qq = 0; qq < 4; ++qq) {
+      int c = c0 + ty + 8 * qq;
+      double v = 0.0;
+      if (r < f && c < nc) {
+        v = (r < nc) ? X[r + (int64_t)c * nc] : -acc[qq];
+        S[r + (int64_t)c * f] = v;
+      }
+      Ts[tx][ty + 8 * qq] = v;
     }
     __syncthreads();
-    for (int e = tid; e < bs * k; e += blockDim.x) W1[j0 * k + e] = tmp[e];
-    __syncthreads();
-    for (int e = tid; e < j0 * k; e += blockDim.x) {
-      int j = e / k, r = e - j * k;
-      const double* Lc = F + j0 + (int64_t)j * f;
-      double sum = 0.0;
-      for (int i = 0; i < bs; ++i) sum = fma(Lc[i], W1[(j0 + i) * k + r], sum);
-      W1[e] -= sum;
+#pragma unroll
+    for (int qq = 0; qq < 4; ++qq) {
+      int rr = r0 + ty + 8 * qq, c = c0 + tx;
+      if (rr < f && c < nc) St[c + (int64_t)rr * nc] = Ts[ty + 8 * qq][tx];
     }
     __syncthreads();
-  }
-  for (int e = tid; e < nc * k; e += blockDim.x) {
-    int i = e / k, r = e - i * k;
-    double v = W1[e];
-    xperm[(int64_t)(first + i) * k + r] = v;
-    X[(int64_t)d.perm[first + i] * xrs + (int64_t)r * xcs] = v;
   }
 }
 
 }  // namespace
 
-struct eigd_factor {
-  eigd_symbolic* sym = nullptr;
-  SymDevHolder* h = nullptr;
-  int max_rhs = 1;
-  double* fronts = nullptr;
-  double* linv = nullptr;
-  double* dval = nullptr;
-  double* dinv = nullptr;
-  double* wbuf = nullptr;
-  double* xperm = nullptr;
-  unsigned long long* amax = nullptr;  // 1 value
-  unsigned long long* info = nullptr;  // 4 values
-  double piv_tol = 1e-11;
-  int64_t bytes = 0;
-  bool attrs_set = false;
-  char* base = nullptr;
-  bool owns = true;
-};
 
 extern "C" int eigd_symbolic_assembly_map_device(eigd_symbolic* s, int n, const int* d_indptr, const int* d_indices,
                                                  int64_t* d_map) {
@@ -664,24 +585,33 @@ extern "C" int eigd_symbolic_assembly_map_device(eigd_symbolic* s, int n, const 
 
 static inline int64_t align256(int64_t b) { return (b + 255) / 256 * 256; }
 
-// sizes (bytes, 256-aligned) of the eight device arrays of a factor, in carving order
-static void factor_layout(const eigd_symbolic* s, int64_t linv_total, int max_rhs, int64_t sz[8]) {
+// sizes (bytes, 256-aligned) of the device arrays of a factor, in carving order
+constexpr int NARR = 15;
+static void factor_layout(const eigd_symbolic* s, const SymDevHolder* h, int max_rhs, int64_t sz[NARR]) {
   int64_t nfront = s->front_off[s->nsuper], sumf = s->w_off[s->nsuper];
+  int kc = std::min(max_rhs, 16);                      // the solve processes at most 16 columns per sweep
   sz[0] = align256(nfront * 8);                        // fronts
-  sz[1] = align256(linv_total * 8);                    // linv
-  sz[2] = align256((int64_t)s->n * 8);                 // dval
-  sz[3] = align256((int64_t)s->n * 8);                 // dinv
-  sz[4] = align256(sumf * max_rhs * 8);                // wbuf
-  sz[5] = align256((int64_t)s->n * max_rhs * 8);       // xperm
-  sz[6] = 256;                                         // amax
-  sz[7] = 256;                                         // info
+  sz[1] = align256(h->linv_total * 8);                 // linv
+  sz[2] = align256(h->xinv_total * 8);                 // xinv
+  sz[3] = align256(h->xinv_total * 8);                 // xtmp
+  sz[4] = align256(h->panel_total * 8);                // sfwd
+  sz[5] = align256(h->panel_total * 8);                // sbwd
+  sz[6] = align256((int64_t)s->n * 8);                 // dval
+  sz[7] = align256((int64_t)s->n * 8);                 // dinv
+  sz[8] = align256(sumf * kc * 8);                     // wbuf
+  sz[9] = align256((int64_t)s->n * kc * 8);            // ybuf
+  sz[10] = align256((int64_t)s->n * kc * 8);           // xperm
+  sz[11] = 256;                                        // amax
+  sz[12] = 256;                                        // info
+  sz[13] = 256;                                        // barrier
+  sz[14] = 0;
 }
 
 extern "C" int64_t eigd_factor_workspace_bytes(eigd_symbolic* s, int max_rhs) {
   if (build_symdev(s)) return -1;
-  int64_t sz[8], tot = 0;
-  factor_layout(s, ((SymDevHolder*)s->dev)->linv_total, std::max(1, max_rhs), sz);
-  for (int i = 0; i < 8; ++i) tot += sz[i];
+  int64_t sz[NARR], tot = 0;
+  factor_layout(s, (SymDevHolder*)s->dev, std::max(1, max_rhs), sz);
+  for (int i = 0; i < NARR; ++i) tot += sz[i];
   return tot + 256;
 }
 
@@ -695,9 +625,9 @@ extern "C" int eigd_factor_create_in(eigd_symbolic* s, int max_rhs, void* d_work
   f->sym = s;
   f->h = (SymDevHolder*)s->dev;
   f->max_rhs = std::max(1, max_rhs);
-  int64_t sz[8], tot = 0;
-  factor_layout(s, f->h->linv_total, f->max_rhs, sz);
-  for (int i = 0; i < 8; ++i) tot += sz[i];
+  int64_t sz[NARR], tot = 0;
+  factor_layout(s, f->h, f->max_rhs, sz);
+  for (int i = 0; i < NARR; ++i) tot += sz[i];
   char* base = nullptr;
   if (d_workspace) {
     base = (char*)(((uintptr_t)d_workspace + 255) / 256 * 256);
@@ -717,12 +647,21 @@ extern "C" int eigd_factor_create_in(eigd_symbolic* s, int max_rhs, void* d_work
   char* p = base;
   f->fronts = (double*)p; p += sz[0];
   f->linv = (double*)p; p += sz[1];
-  f->dval = (double*)p; p += sz[2];
-  f->dinv = (double*)p; p += sz[3];
-  f->wbuf = (double*)p; p += sz[4];
-  f->xperm = (double*)p; p += sz[5];
-  f->amax = (unsigned long long*)p; p += sz[6];
-  f->info = (unsigned long long*)p;
+  f->xinv = (double*)p; p += sz[2];
+  f->xtmp = (double*)p; p += sz[3];
+  f->sfwd = (double*)p; p += sz[4];
+  f->sbwd = (double*)p; p += sz[5];
+  f->dval = (double*)p; p += sz[6];
+  f->dinv = (double*)p; p += sz[7];
+  f->wbuf = (double*)p; p += sz[8];
+  f->ybuf = (double*)p; p += sz[9];
+  f->xperm = (double*)p; p += sz[10];
+  f->amax = (unsigned long long*)p; p += sz[11];
+  f->info = (unsigned long long*)p; p += sz[12];
+  f->barrier = (unsigned long long*)p;
+  f->bar_base = 0;
+  cudaError_t eb = cudaMemsetAsync(f->barrier, 0, 256, g_eigd_stream);
+  if (eb != cudaSuccess) { eigd_set_error("factor_create: memset -> %s", cudaGetErrorString(eb)); eigd_factor_destroy(f); return 100 + (int)eb; }
   *out = f;
   return 0;
 }
@@ -746,6 +685,7 @@ extern "C" int eigd_factor_numeric(eigd_factor* f, int64_t nnz, const double* d_
   EIGD_CUDA(cudaMemsetAsync(f->fronts, 0, (size_t)nfront * 8, g_eigd_stream));
   EIGD_CUDA(cudaMemsetAsync(f->amax, 0, 8, g_eigd_stream));
   EIGD_CUDA(cudaMemsetAsync(f->info, 0, 32, g_eigd_stream));
+  EIGD_CUDA(cudaMemsetAsync(f->xinv, 0, (size_t)std::max<int64_t>(h->xinv_total, 1) * 8, g_eigd_stream));
   int g = (int)std::min<int64_t>((nnz + 255) / 256, 148 * 16);
   if (g < 1) g = 1;
   EIGD_LAUNCH(absmax_kernel, g, 256, 0, nnz, d_vals, f->amax);
@@ -759,6 +699,10 @@ extern "C" int eigd_factor_numeric(eigd_factor* f, int64_t nnz, const double* d_
       case 1: EIGD_LAUNCH(diag_factor_kernel, L.count, 256, 0, h->d, t, L.kb, f->fronts, f->linv, f->dval, f->dinv, f->amax, f->piv_tol, f->info); break;
       case 2: EIGD_LAUNCH(trsm_kernel, L.count, TRSM_ROWS, 0, h->d, t, L.kb, f->fronts, f->linv, f->dinv); break;
       case 3: EIGD_LAUNCH(trailing_update_kernel, L.count, 256, 0, h->d, t, L.kb, f->fronts, f->dval); break;
+      case 4: EIGD_LAUNCH(inverse_init_kernel, L.count, 256, 0, h->d, t, f->linv, f->xinv); break;
+      case 5: EIGD_LAUNCH(inverse_ca_kernel, L.count, 256, 0, h->d, t, NB << L.kb, f->fronts, f->xinv, f->xtmp); break;
+      case 6: EIGD_LAUNCH(inverse_bt_kernel, L.count, 256, 0, h->d, t, NB << L.kb, f->xinv, f->xtmp); break;
+      case 7: EIGD_LAUNCH(panel_build_kernel, L.count, 256, 0, h->d, t, f->fronts, f->xinv, f->sfwd, f->sbwd); break;
       default: break;
     }
     EIGD_CHECK_LAUNCH();
@@ -774,51 +718,3 @@ extern "C" int eigd_factor_info(eigd_factor* f, int64_t* info3) {
   return 0;
 }
 
-template <int KT>
-static int solve_chunk(eigd_factor* f, const double* B, int64_t brs, int64_t bcs, double* X, int64_t xrs, int64_t xcs, int k) {
-  SymDevHolder* h = f->h;
-  size_t smem = (size_t)f->sym->maxcols * k * sizeof(double);
-  if (!f->attrs_set) {
-    int maxs = 256 * 32 * 8;
-    EIGD_CUDA(cudaFuncSetAttribute(fwd_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
-    EIGD_CUDA(cudaFuncSetAttribute(bwd_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
-    EIGD_CUDA(cudaFuncSetAttribute(fwd_update_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
-    EIGD_CUDA(cudaFuncSetAttribute(fwd_update_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
-    EIGD_CUDA(cudaFuncSetAttribute(fwd_update_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
-    EIGD_CUDA(cudaFuncSetAttribute(fwd_update_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
-    EIGD_CUDA(cudaFuncSetAttribute(fwd_update_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
-    f->attrs_set = true;
-  }
-  for (const Launch& L : h->fwd_plan) {
-    const int2* t = h->tasks + L.off;
-    if (L.kind == 4) EIGD_LAUNCH(fwd_diag_kernel, L.count, 256, smem, h->d, t, f->fronts, f->linv, f->wbuf, B, brs, bcs, k);
-    else EIGD_LAUNCH(fwd_update_kernel<KT>, L.count, FWD_ROWS, smem, h->d, t, f->fronts, f->wbuf, k);
-    EIGD_CHECK_LAUNCH();
-  }
-  for (const Launch& L : h->bwd_plan) {
-    const int2* t = h->tasks + L.off;
-    if (L.kind == 6) EIGD_LAUNCH(bwd_update_kernel<KT>, L.count, BWD_COLS * 32, 0, h->d, t, f->fronts, f->wbuf, f->xperm, f->dinv, k);
-    else EIGD_LAUNCH(bwd_diag_kernel, L.count, 256, smem, h->d, t, f->fronts, f->linv, f->wbuf, f->xperm, X, xrs, xcs, k);
-    EIGD_CHECK_LAUNCH();
-  }
-  return 0;
-}
-
-extern "C" int eigd_factor_solve(eigd_factor* f, const double* B, int64_t brs, int64_t bcs, double* X, int64_t xrs,
-                                 int64_t xcs, int k) {
-  if (k <= 0) return 0;
-  int chunk = std::min(32, f->max_rhs);
-  for (int c0 = 0; c0 < k; c0 += chunk) {
-    int kc = std::min(chunk, k - c0);
-    const double* Bc = B + (int64_t)c0 * bcs;
-    double* Xc = X + (int64_t)c0 * xcs;
-    int rc;
-    if (kc == 1) rc = solve_chunk<1>(f, Bc, brs, bcs, Xc, xrs, xcs, kc);
-    else if (kc <= 4) rc = solve_chunk<4>(f, Bc, brs, bcs, Xc, xrs, xcs, kc);
-    else if (kc <= 8) rc = solve_chunk<8>(f, Bc, brs, bcs, Xc, xrs, xcs, kc);
-    else if (kc <= 16) rc = solve_chunk<16>(f, Bc, brs, bcs, Xc, xrs, xcs, kc);
-    else rc = solve_chunk<32>(f, Bc, brs, bcs, Xc, xrs, xcs, kc);
-    if (rc) return rc;
-  }
-  return 0;
-}

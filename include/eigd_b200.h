@@ -93,6 +93,12 @@ int eigd_symbolic_assembly_map_host(const eigd_symbolic* s, int n, const int* in
 /* the same map computed by the CUDA integer kernel (device CSR in, device map out) */
 int eigd_symbolic_assembly_map_device(eigd_symbolic* s, int n, const int* d_indptr, const int* d_indices, int64_t* d_map);
 
+/* inspection of the host-built plan of the persistent solve kernel (tests): which = 0 soff[nsuper+1],
+ * 1 pull2[2*sum_front], 2 overflow list, 3 tile records (7 values each: first, nc, nb, tile, soff,
+ * w_off, row_off), 4 phases (5 values each: dir, ws, ntiles, level, tile_off).  target_warps = resident
+ * warps the plan is balanced for.  Returns the element count; copies min(count, cap) values. */
+int64_t eigd_solve_plan_get(const eigd_symbolic* s, int target_warps, int which, int64_t* out, int64_t cap);
+
 int eigd_factor_create(eigd_symbolic* s, int max_rhs, eigd_factor** out);
 /* same, with every device array carved out of a caller-owned buffer of eigd_factor_workspace_bytes()
  * bytes (a torch tensor, so that the caching allocator recycles it: no cudaMalloc / cudaFree per design) */
