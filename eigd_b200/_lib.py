@@ -36,7 +36,7 @@ SIGNATURES = {
     "eigd_symbolic_get": (c_i64, [c_ptr, c_int, c_ptr, c_i64]),
     "eigd_symbolic_assembly_map_host": (c_int, [c_ptr, c_int, c_ptr, c_ptr, c_ptr]),
     "eigd_symbolic_assembly_map_device": (c_int, [c_ptr, c_int, c_ptr, c_ptr, c_ptr]),
-    "eigd_solve_plan_get": (c_i64, [c_ptr, c_int, c_int, c_ptr, c_i64]),
+    "eigd_solve_plan_get": (c_i64, [c_ptr, c_int, c_int, c_int, c_int, c_ptr, c_i64]),
     "eigd_factor_create": (c_int, [c_ptr, c_int, c_ptr]),
     "eigd_factor_workspace_bytes": (c_i64, [c_ptr, c_int]),
     "eigd_factor_create_in": (c_int, [c_ptr, c_int, c_ptr, c_i64, c_ptr]),
@@ -45,6 +45,8 @@ SIGNATURES = {
     "eigd_factor_info": (c_int, [c_ptr, c_ptr]),
     "eigd_factor_solve": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_i64, c_i64, c_int]),
     "eigd_factor_bytes": (c_i64, [c_ptr]),
+    "eigd_solve_set_phase_times": (c_int, [c_ptr]),
+    "eigd_solve_num_phases": (c_int, [c_ptr]),
     "eigd_q4_assemble": (c_int, [c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_ptr]),
     "eigd_q4_quadforms": (c_int, [c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_ptr, c_ptr, c_dbl, c_dbl, c_ptr]),
     "eigd_q4_material": (c_int, [c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),

@@ -109,13 +109,128 @@ gemm_tn_partial(int64_t n, int k1, int k2, const double* __restrict__ X, int64_t
   }
 }
 
-// C[a*ldc + b] = sum_cta partial[cta][a*k2+b]
+// C[a*ldc + b] = sum_cta partial[cta][a*k2+b]; one warp per output, lanes stride over the CTAs and meet
+// in a shuffle tree (fixed order: deterministic)
 __global__ void reduce_partials(int ncta, int k1, int k2, const double* __restrict__ partial, double* __restrict__ C, int ldc) {
-  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
   if (e >= k1 * k2) return;
   double s = 0.0;
-  for (int c = 0; c < ncta; ++c) s += partial[(int64_t)c * (k1 * k2) + e];
-  C[(e / k2) * ldc + (e % k2)] = s;
+  for (int c = lane; c < ncta; c += 32) s += partial[(int64_t)c * (k1 * k2) + e];
+  s = warp_sum(s);
+  if (lane == 0) C[(e / k2) * ldc + (e % k2)] = s;
+}
+
+// ---- Krylov-basis kernels: the basis is stored one vector per row (row a at V + a*ldv), w is a
+// contiguous n-vector.  These are the two halves of a classical Gram-Schmidt pass
+// (eigd/eigenvector_derivatives.py:1529-1538; ARPACK dsaitr steps 3-4): h = V^T w, w -= V h.
+constexpr int BD_THREADS = 256;
+constexpr int BD_EPT = 4;                       // elements of w per thread
+constexpr int BD_CHUNK = BD_THREADS * BD_EPT;   // per CTA
+constexpr int BD_ROWS = 8;                      // basis rows in flight per thread
+constexpr int BD_JMAX = 128;
+
+// out[a] = sum_i V[a][i] * w[i], a < j.  CTA c owns elements [c*BD_CHUNK, (c+1)*BD_CHUNK): w lives in
+// registers, eight basis rows are streamed at a time (32 independent 8-byte loads per thread).  Partial
+// sums go to partial[cta][a]; the last CTA to finish (ticket) adds them in a fixed order, so the result
+// is bitwise reproducible and no second launch is needed.
+__global__ void __launch_bounds__(BD_THREADS)
+basis_dots_kernel(int64_t n, int j, const double* __restrict__ V, int64_t ldv, const double* __restrict__ w,
+                  double* __restrict__ partial, double* __restrict__ out, unsigned int* __restrict__ ticket) {
+  __shared__ double red[BD_THREADS / 32][BD_JMAX];
+  __shared__ bool last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t i0 = (int64_t)blockIdx.x * BD_CHUNK + tid;
+  double wv[BD_EPT];
+#pragma unroll
+  for (int q = 0; q < BD_EPT; ++q) {
+    int64_t i = i0 + (int64_t)q * BD_THREADS;
+    wv[q] = (i < n) ? w[i] : 0.0;
+  }
+  for (int a0 = 0; a0 < j; a0 += BD_ROWS) {
+    double v[BD_ROWS][BD_EPT];
+#pragma unroll
+    for (int r = 0; r < BD_ROWS; ++r) {
+      const double* row = V + (int64_t)min(a0 + r, j - 1) * ldv;
+#pragma unroll
+      for (int q = 0; q < BD_EPT; ++q) {
+        int64_t i = i0 + (int64_t)q * BD_THREADS;
+        v[r][q] = (i < n) ? __ldg(row + i) : 0.0;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < BD_ROWS; ++r) {
+      double s = 0.0;
+#pragma unroll
+      for (int q = 0; q < BD_EPT; ++q) s = fma(v[r][q], wv[q], s);
+      s = warp_sum(s);
+      if (lane == 0 && a0 + r < j) red[warp][a0 + r] = s;
+    }
+  }
+  __syncthreads();
+  if (tid < j) {
+    double s = 0.0;
+#pragma unroll
+    for (int g = 0; g < BD_THREADS / 32; ++g) s += red[g][tid];
+    partial[(int64_t)blockIdx.x * BD_JMAX + tid] = s;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  // 4 lanes per output row, each adds every 4th CTA's partial; rows beyond 64 in a second round
+  const int ncta = gridDim.x;
+  for (int a = tid >> 2; a < j; a += BD_THREADS >> 2) {
+    const int q = tid & 3;
+    double s = 0.0;
+    for (int c = q; c < ncta; c += 4) s += __ldcg(partial + (int64_t)c * BD_JMAX + a);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    if (q == 0) out[a] = s;
+  }
+  if (tid == 0) *ticket = 0u;
+}
+
+// w[i] += sign * sum_a h[a] * V[a][i]; optionally also writes the result to a second vector (w2)
+__global__ void __launch_bounds__(BD_THREADS)
+basis_axpy_kernel(int64_t n, int j, const double* __restrict__ V, int64_t ldv, const double* __restrict__ h, double sign,
+                  double* __restrict__ w) {
+  __shared__ double hs[BD_JMAX];
+  const int tid = threadIdx.x;
+  if (tid < j) hs[tid] = sign * h[tid];
+  __syncthreads();
+  const int64_t i0 = (int64_t)blockIdx.x * BD_CHUNK + tid;
+  double acc[BD_EPT];
+#pragma unroll
+  for (int q = 0; q < BD_EPT; ++q) {
+    int64_t i = i0 + (int64_t)q * BD_THREADS;
+    acc[q] = (i < n) ? w[i] : 0.0;
+  }
+  for (int a0 = 0; a0 < j; a0 += BD_ROWS) {
+    double v[BD_ROWS][BD_EPT];
+#pragma unroll
+    for (int r = 0; r < BD_ROWS; ++r) {
+      const double* row = V + (int64_t)min(a0 + r, j - 1) * ldv;
+#pragma unroll
+      for (int q = 0; q < BD_EPT; ++q) {
+        int64_t i = i0 + (int64_t)q * BD_THREADS;
+        v[r][q] = (i < n) ? __ldg(row + i) : 0.0;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < BD_ROWS; ++r) {
+      const double hr = (a0 + r < j) ? hs[a0 + r] : 0.0;
+#pragma unroll
+      for (int q = 0; q < BD_EPT; ++q) acc[q] = fma(hr, v[r][q], acc[q]);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < BD_EPT; ++q) {
+    int64_t i = i0 + (int64_t)q * BD_THREADS;
+    if (i < n) w[i] = acc[q];
+  }
 }
 
 constexpr int NN_R = 32;
@@ -224,12 +339,32 @@ __global__ void axpby_kernel(int64_t len, double a, const double* __restrict__ x
     out[e] = a * x[e] + (b == 0.0 ? 0.0 : b * y[e]);
 }
 
+__device__ unsigned int g_basis_ticket = 0;
+
 inline int tn_grid(int64_t n) {
   int64_t t = (n + TN_R - 1) / TN_R;
   return (int)(t < RED_MAX_CTAS ? (t < 1 ? 1 : t) : RED_MAX_CTAS);
 }
 
 }  // namespace
+
+int eigd_basis_dots(int64_t n, int j, const double* V, int64_t ldv, const double* w, double* out, double* work) {
+  unsigned int* ticket = nullptr;
+  EIGD_CUDA(cudaGetSymbolAddress((void**)&ticket, g_basis_ticket));
+  int grid = (int)((n + BD_CHUNK - 1) / BD_CHUNK);
+  EIGD_LAUNCH(basis_dots_kernel, grid, BD_THREADS, 0, n, j, V, ldv, w, work, out, ticket);
+  EIGD_CHECK_LAUNCH();
+  return 0;
+}
+
+// w += alpha * sum_a S[a*lds] V[a]
+int eigd_basis_axpy(int64_t n, int j, const double* V, int64_t ldv, const double* S, int lds, double alpha, double* w) {
+  (void)lds;
+  int grid = (int)((n + BD_CHUNK - 1) / BD_CHUNK);
+  EIGD_LAUNCH(basis_axpy_kernel, grid, BD_THREADS, 0, n, j, V, ldv, S, alpha, w);
+  EIGD_CHECK_LAUNCH();
+  return 0;
+}
 
 extern "C" int64_t eigd_gemm_tn_workspace(int k1, int k2) {
   (void)k1; (void)k2;
@@ -239,6 +374,10 @@ extern "C" int64_t eigd_gemm_tn_workspace(int k1, int k2) {
 extern "C" int eigd_gemm_tn(int64_t n, int k1, int k2, const double* X, int64_t xrs, int64_t xcs, const double* Y,
                             int64_t yrs, int64_t ycs, double* C, int ldc, double* work) {
   if (n <= 0 || k1 <= 0 || k2 <= 0) return 0;
+  if (k2 == 1 && xrs == 1 && yrs == 1 && (ldc == 1 || k1 == 1) && k1 <= BD_JMAX) {     // Krylov basis (one vector per row) times a vector
+    int64_t ncta = (n + BD_CHUNK - 1) / BD_CHUNK;
+    if (ncta * BD_JMAX <= eigd_gemm_tn_workspace(k1, k2)) return eigd_basis_dots(n, k1, X, xcs, Y, C, work);
+  }
   for (int a0 = 0; a0 < k1; a0 += TN_KMAX) {
     int ka = min(TN_KMAX, k1 - a0);
     for (int b0 = 0; b0 < k2; b0 += TN_KMAX) {
@@ -250,7 +389,7 @@ extern "C" int eigd_gemm_tn(int64_t n, int k1, int k2, const double* X, int64_t 
       EIGD_LAUNCH(gemm_tn_partial, grid, TN_THREADS, smem, n, ka, kb, X + (int64_t)a0 * xcs, xrs, xcs,
                   Y + (int64_t)b0 * ycs, yrs, ycs, work);
       EIGD_CHECK_LAUNCH();
-      EIGD_LAUNCH(reduce_partials, (ka * kb + 255) / 256, 256, 0, grid, ka, kb, work, C + (int64_t)a0 * ldc + b0, ldc);
+      EIGD_LAUNCH(reduce_partials, (ka * kb + 7) / 8, 256, 0, grid, ka, kb, work, C + (int64_t)a0 * ldc + b0, ldc);
       EIGD_CHECK_LAUNCH();
     }
   }
@@ -265,6 +404,7 @@ extern "C" int eigd_gemm_nn(int64_t n, int k1, int k2, double alpha, const doubl
   if (k1 <= 0) {  // Y = beta*Y
     return 0;
   }
+  if (k2 == 1 && xrs == 1 && yrs == 1 && beta == 1.0 && k1 <= BD_JMAX && (lds == 1 || k1 == 1)) return eigd_basis_axpy(n, k1, X, xcs, S, lds, alpha, Y);
   for (int b0 = 0; b0 < k2; b0 += NN_K2MAX) {
     int kb = min(NN_K2MAX, k2 - b0);
     for (int a0 = 0; a0 < k1; a0 += NN_K1MAX) {
@@ -287,7 +427,7 @@ extern "C" int eigd_col_dot(int64_t n, int k, const double* X, int64_t xrs, int6
     int grid = (int)(want < 1 ? 1 : (want > RED_MAX_CTAS ? RED_MAX_CTAS : want));
     EIGD_LAUNCH(col_dot_partial, grid, 256, 0, n, kc, X + (int64_t)c0 * xcs, xrs, xcs, Y + (int64_t)c0 * ycs, yrs, ycs, work);
     EIGD_CHECK_LAUNCH();
-    EIGD_LAUNCH(reduce_partials, 1, 64, 0, grid, 1, kc, work, out + c0, kc);
+    EIGD_LAUNCH(reduce_partials, (kc + 7) / 8, 256, 0, grid, 1, kc, work, out + c0, kc);
     EIGD_CHECK_LAUNCH();
   }
   return 0;

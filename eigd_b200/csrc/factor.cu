@@ -586,7 +586,7 @@ extern "C" int eigd_symbolic_assembly_map_device(eigd_symbolic* s, int n, const 
 static inline int64_t align256(int64_t b) { return (b + 255) / 256 * 256; }
 
 // sizes (bytes, 256-aligned) of the device arrays of a factor, in carving order
-constexpr int NARR = 15;
+constexpr int NARR = 16;
 static void factor_layout(const eigd_symbolic* s, const SymDevHolder* h, int max_rhs, int64_t sz[NARR]) {
   int64_t nfront = s->front_off[s->nsuper], sumf = s->w_off[s->nsuper];
   int kc = std::min(max_rhs, 16);                      // the solve processes at most 16 columns per sweep
@@ -598,13 +598,14 @@ static void factor_layout(const eigd_symbolic* s, const SymDevHolder* h, int max
   sz[5] = align256(h->panel_total * 8);                // sbwd
   sz[6] = align256((int64_t)s->n * 8);                 // dval
   sz[7] = align256((int64_t)s->n * 8);                 // dinv
-  sz[8] = align256(sumf * kc * 8);                     // wbuf
+  sz[8] = align256(3 * sumf * kc * 8);                 // wbuf: three child slabs, one plane per right-hand side
   sz[9] = align256((int64_t)s->n * kc * 8);            // ybuf
   sz[10] = align256((int64_t)s->n * kc * 8);           // xperm
   sz[11] = 256;                                        // amax
   sz[12] = 256;                                        // info
   sz[13] = 256;                                        // barrier
-  sz[14] = 0;
+  sz[14] = align256((int64_t)s->n * kc * 8);           // bperm
+  sz[15] = 0;
 }
 
 extern "C" int64_t eigd_factor_workspace_bytes(eigd_symbolic* s, int max_rhs) {
@@ -658,9 +659,12 @@ extern "C" int eigd_factor_create_in(eigd_symbolic* s, int max_rhs, void* d_work
   f->xperm = (double*)p; p += sz[10];
   f->amax = (unsigned long long*)p; p += sz[11];
   f->info = (unsigned long long*)p; p += sz[12];
-  f->barrier = (unsigned long long*)p;
+  f->barrier = (unsigned long long*)p; p += sz[13];
+  f->bperm = (double*)p;
   f->bar_base = 0;
-  cudaError_t eb = cudaMemsetAsync(f->barrier, 0, 256, g_eigd_stream);
+  // slab rows that no child writes must read as zero for ever; the written ones are rewritten by every solve
+  cudaError_t eb = cudaMemsetAsync(f->wbuf, 0, (size_t)sz[8], g_eigd_stream);
+  if (eb == cudaSuccess) eb = cudaMemsetAsync(f->barrier, 0, 256, g_eigd_stream);
   if (eb != cudaSuccess) { eigd_set_error("factor_create: memset -> %s", cudaGetErrorString(eb)); eigd_factor_destroy(f); return 100 + (int)eb; }
   *out = f;
   return 0;

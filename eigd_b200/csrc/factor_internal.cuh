@@ -39,8 +39,9 @@ struct Launch {
 struct SolvePlanDev {
   TileRec* tiles = nullptr;
   PhaseRec* phases = nullptr;
-  int2* pull2 = nullptr;
+  int* ovf_row = nullptr;
   int* ovf = nullptr;
+  int* sub_ptr = nullptr;
   int nphases = 0;
   int grid = 0;               // CTAs of the cooperative launch
   std::vector<PhaseRec> host_phases;
@@ -69,7 +70,8 @@ struct eigd_factor {
   double* sbwd = nullptr;     // S^T, nc x f column-major
   double* dval = nullptr;
   double* dinv = nullptr;
-  double* wbuf = nullptr;     // forward-sweep update vectors, (sum of front sizes) x k
+  double* wbuf = nullptr;     // forward-sweep update vectors: 3 slabs x kmax planes x (sum of front sizes)
+  double* bperm = nullptr;    // right-hand side in the permuted ordering, n x k
   double* ybuf = nullptr;     // D^-1 L^-1 b in the permuted ordering, n x k
   double* xperm = nullptr;    // solution in the permuted ordering, n x k
   unsigned long long* amax = nullptr;   // 1 value

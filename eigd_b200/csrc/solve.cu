@@ -26,27 +26,35 @@
 
 namespace {
 
+constexpr int MAX_PHASES_SMEM = 96;
+
 struct SolveArgs {
   const TileRec* tiles;
   const PhaseRec* phases;
   int nphases;
-  const int2* pull2;
+  const int* ovf_row;
   const int* ovf;
+  const int* sub_ptr;
   const int* perm;
   const int* sn_rows;
+  const int* rel;
   const double* sfwd;
   const double* sbwd;
   const double* dinv;
-  double* wbuf;
+  double* wbuf;          // three slabs x kmax planes x sumf rows
+  int64_t sumf;          // rows per plane
+  int64_t slab_stride;   // kmax * sumf
+  double* bperm;         // permuted right-hand side, n x k
   double* ybuf;
   double* xperm;
   const double* B;
   int64_t brs, bcs;
   double* X;
   int64_t xrs, xcs;
-  int k;
+  int n, k;
   unsigned long long* barrier;
   unsigned long long bar_base;
+  unsigned long long* times;      // developer profiling: %globaltimer of CTA 0 after every phase (NULL: off)
 };
 
 // vectors produced earlier in the same launch by other SMs are read through L2 (ld.global.cg): L1 is
@@ -59,39 +67,63 @@ __device__ __forceinline__ void add_row(const double* __restrict__ base, int64_t
     if (r < k) v[r] += __ldcg(p + r);
 }
 
-// v += sum of the forward-sweep updates addressed to w-row t (fixed order: deterministic)
+// v += the forward-sweep updates addressed to w-row t: slab 0 + slab 1 (+ overflow list), fixed order
 template <int KT>
-__device__ __forceinline__ void pull_add(const SolveArgs& a, int64_t t, double* v) {
-  const int2 pp = __ldg(&a.pull2[t]);
-  if (pp.x >= 0) add_row<KT>(a.wbuf, pp.x, a.k, v);
-  if (pp.y >= 0) add_row<KT>(a.wbuf, pp.y, a.k, v);
-  else if (pp.y <= -2) {
-    const int o = -2 - pp.y;
-    const int cnt = __ldg(&a.ovf[o]);
-    for (int q = 0; q < cnt; ++q) add_row<KT>(a.wbuf, __ldg(&a.ovf[o + 1 + q]), a.k, v);
+__device__ __forceinline__ void child_add(const SolveArgs& a, int64_t t, int64_t link, double* v) {
+  if (!(link & LINK_HAS_CHILDREN)) return;
+  const double* p0 = a.wbuf + t;
+  const double* p1 = p0 + a.slab_stride;
+#pragma unroll
+  for (int r = 0; r < KT; ++r)
+    if (r < a.k) v[r] += __ldcg(p0 + (int64_t)r * a.sumf) + __ldcg(p1 + (int64_t)r * a.sumf);
+  if (link & LINK_HAS_OVF) {
+    const int o = __ldg(&a.ovf_row[t]);
+    if (o >= 0) {
+      const int cnt = __ldg(&a.ovf[o]);
+      const double* p2 = a.wbuf + 2 * a.slab_stride;
+      for (int q = 0; q < cnt; ++q) {
+        const int64_t src = __ldg(&a.ovf[o + 1 + q]);
+#pragma unroll
+        for (int r = 0; r < KT; ++r)
+          if (r < a.k) v[r] += __ldcg(p2 + (int64_t)r * a.sumf + src);
+      }
+    }
   }
 }
 
-__device__ __forceinline__ TileRec load_tile(const TileRec* p) {
-  const int4* q = reinterpret_cast<const int4*>(p);
-  int4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+__device__ __forceinline__ TileRec unpack_tile(int4 a, int4 b, int4 c) {
   TileRec t;
   t.first = a.x; t.nc = a.y; t.nb = a.z; t.tile = a.w;
   t.soff = ((int64_t)(unsigned)b.x) | ((int64_t)b.y << 32);
   t.w_off = ((int64_t)(unsigned)b.z) | ((int64_t)b.w << 32);
   t.row_off = ((int64_t)(unsigned)c.x) | ((int64_t)c.y << 32);
-  t.pad = 0;
+  t.link = ((int64_t)(unsigned)c.z) | ((int64_t)c.w << 32);
   return t;
 }
 
+__device__ __forceinline__ TileRec load_tile(const TileRec* p) {
+  const int4* q = reinterpret_cast<const int4*>(p);
+  return unpack_tile(__ldg(q), __ldg(q + 1), __ldg(q + 2));
+}
+
 // acc += M[out, c0:c1) * in[c0:c1) for this lane's output; M column-major with leading dimension ld.
-// stage_fn(c, v) fills v[0:k) with input vector entry c (lane-parallel), the chunk is then shared
-// through the warp's staging buffer.
+// stage_fn(c, v) fills v[0:k) with input vector entry c (lane-parallel over the chunk of 32 columns),
+// the chunk is then shared through the warp's staging buffer.  Memory-level parallelism comes from the
+// instruction stream, not from occupancy: the panel entries of a sub-chunk are requested back to back
+// (MC independent 8-byte loads per lane, 256 B per warp each) BEFORE the gather of the input vector, so
+// one DRAM round trip covers MC columns.
 template <int KT, class StageFn>
 __device__ __forceinline__ void warp_panel_product(const double* __restrict__ M, int64_t ld, int c0, int c1, int lane,
                                                    double* stage, double* acc, StageFn stage_fn) {
+  constexpr int MC = KT <= 2 ? 32 : (KT <= 8 ? 16 : 8);
+  constexpr int g = 0, nks = 1;
   for (int cc = c0; cc < c1; cc += 32) {
     const int ncol = min(32, c1 - cc);
+    const double* Mc = M + (int64_t)(cc + g) * ld;
+    const int64_t step = (int64_t)nks * ld;
+    double m[MC];
+#pragma unroll
+    for (int j = 0; j < MC; ++j) m[j] = (g + j * nks < ncol) ? __ldg(Mc + j * step) : 0.0;
     double v[KT];
 #pragma unroll
     for (int r = 0; r < KT; ++r) v[r] = 0.0;
@@ -99,12 +131,19 @@ __device__ __forceinline__ void warp_panel_product(const double* __restrict__ M,
 #pragma unroll
     for (int r = 0; r < KT; ++r) stage[r * 32 + lane] = v[r];
     __syncwarp();
-    const double* Mc = M + (int64_t)cc * ld;
-#pragma unroll 8
-    for (int t = 0; t < ncol; ++t) {
-      const double m = __ldg(Mc + (int64_t)t * ld);
 #pragma unroll
-      for (int r = 0; r < KT; ++r) acc[r] = fma(m, stage[r * 32 + t], acc[r]);
+    for (int j = 0; j < MC; ++j)
+#pragma unroll
+      for (int r = 0; r < KT; ++r) acc[r] = fma(m[j], stage[r * 32 + ((g + j * nks) & 31)], acc[r]);
+    if (MC < 32) {
+      for (int j0 = MC; g + j0 * nks < ncol; j0 += MC) {          // warp-uniform trip count is not needed: no sync inside
+#pragma unroll
+        for (int j = 0; j < MC; ++j) m[j] = (g + (j0 + j) * nks < ncol) ? __ldg(Mc + (j0 + j) * step) : 0.0;
+#pragma unroll
+        for (int j = 0; j < MC; ++j)
+#pragma unroll
+          for (int r = 0; r < KT; ++r) acc[r] = fma(m[j], stage[r * 32 + ((g + (j0 + j) * nks) & 31)], acc[r]);
+      }
     }
     __syncwarp();
   }
@@ -113,110 +152,199 @@ __device__ __forceinline__ void warp_panel_product(const double* __restrict__ M,
 __device__ __forceinline__ void grid_barrier(unsigned long long* ctr, unsigned long long target) {
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(ctr, 1ULL);
     unsigned long long v;
+    asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(ctr) : "memory");
     do {
       asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(ctr) : "memory");
     } while (v < target);
-    __threadfence();
   }
   __syncthreads();
+}
+
+// the products of one warp tile: slice `slice` of `ws` of the reduction dimension.
+// use_perm: the right-hand side is gathered from B through perm (first phase; later phases read the
+// permuted copy written during the first one)
+template <int KT>
+__device__ __forceinline__ void tile_compute(const SolveArgs& a, int dir, bool use_perm, const TileRec& tr, int lane,
+                                             int slice, int ws, double* stage, double* acc) {
+  constexpr int to = SOLVE_TILE;
+  const int k = a.k;
+  const int nc = tr.nc, f = tr.nc + tr.nb;
+  const int o0 = tr.tile * to;
+  const int out = o0 + (lane % to);
+  if (dir == 0) {
+    // ---- forward: outputs are front rows; acc = S[row, 0:cend) w1 (+ the children's updates of the row)
+    if (slice == 0 && lane < to && out >= nc && out < f) child_add<KT>(a, tr.w_off + out, tr.link, acc);
+    const int cend = min(nc, o0 + to);                  // S is lower triangular inside the pivot rows
+    const int per = (cend + ws - 1) / ws;
+    const int c0 = slice * per, c1 = min(cend, c0 + per);
+    const double* M = a.sfwd + tr.soff + min(out, f - 1);
+    warp_panel_product<KT>(M, f, c0, c1, lane, stage, acc, [&](int c, double* v) {
+      if (use_perm) {
+        const int64_t po = __ldg(&a.perm[tr.first + c]);
+        const double* bp = a.B + po * a.brs;
+#pragma unroll
+        for (int r = 0; r < KT; ++r)
+          if (r < k) v[r] = bp[(int64_t)r * a.bcs];
+      } else {
+        add_row<KT>(a.bperm, tr.first + c, k, v);
+      }
+      child_add<KT>(a, tr.w_off + c, tr.link, v);
+    });
+  } else {
+    // ---- backward: outputs are pivot columns; acc = S^T[col, o0:f) [z1 ; x2]
+    const int len = f - o0;
+    const int per = (len + ws - 1) / ws;
+    const int i0 = o0 + slice * per, i1 = min(f, i0 + per);
+    const double* M = a.sbwd + tr.soff + min(out, nc - 1);
+    warp_panel_product<KT>(M, nc, i0, i1, lane, stage, acc, [&](int i, double* v) {
+      if (i < nc) add_row<KT>(a.ybuf, tr.first + i, k, v);
+      else add_row<KT>(a.xperm, __ldg(&a.sn_rows[tr.row_off + i - nc]), k, v);
+    });
+  }
+}
+
+template <int KT>
+__device__ __forceinline__ void tile_store(const SolveArgs& a, int dir, const TileRec& tr, int lane, const double* acc) {
+  const int k = a.k;
+  const int nc = tr.nc, f = tr.nc + tr.nb;
+  const int out = tr.tile * SOLVE_TILE + lane;
+  if (dir == 0) {
+    if (out < nc) {
+      const double di = __ldg(&a.dinv[tr.first + out]);
+      double* y = a.ybuf + (int64_t)(tr.first + out) * k;
+#pragma unroll
+      for (int r = 0; r < KT; ++r)
+        if (r < k) y[r] = di * acc[r];
+    } else if (out < f) {
+      const int slab = (int)((tr.link >> LINK_SLAB_SHIFT) & 0xff);
+      int64_t dst;                                            // row in the plane of the destination slab
+      if (slab < 2) dst = slab * a.slab_stride + (tr.link & LINK_WOFF_MASK) + __ldg(&a.rel[tr.row_off + out - nc]);
+      else dst = 2 * a.slab_stride + tr.w_off + out;
+      double* w = a.wbuf + dst;
+#pragma unroll
+      for (int r = 0; r < KT; ++r)
+        if (r < k) w[(int64_t)r * a.sumf] = acc[r];
+    }
+  } else if (out < nc) {
+    double* xp = a.xperm + (int64_t)(tr.first + out) * k;
+    double* xo = a.X + (int64_t)__ldg(&a.perm[tr.first + out]) * a.xrs;
+#pragma unroll
+    for (int r = 0; r < KT; ++r)
+      if (r < k) { xp[r] = acc[r]; xo[(int64_t)r * a.xcs] = acc[r]; }
+  }
 }
 
 template <int KT>
 __global__ void __launch_bounds__(SOLVE_WARPS * 32, 1) solve_kernel(SolveArgs a) {
   extern __shared__ double smem[];
+  __shared__ PhaseRec s_phase[MAX_PHASES_SMEM];
+  __shared__ int4 s_next[SOLVE_WARPS][3];                  // first tile record of the next phase, per warp
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double* stage = smem + warp * (32 * KT);                 // [KT][32] per warp
   double* part = smem + SOLVE_WARPS * 32 * KT;             // [SOLVE_WARPS][KT][32] partial sums
-  const int k = a.k;
   unsigned long long target = a.bar_base;
+  if (a.times && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    a.times[0] = t;
+  }
+  {
+    const int4* src = reinterpret_cast<const int4*>(a.phases);
+    int4* dst = reinterpret_cast<int4*>(s_phase);
+    for (int e = threadIdx.x; e < 2 * min(a.nphases, MAX_PHASES_SMEM); e += blockDim.x) dst[e] = __ldg(src + e);
+  }
+  __syncthreads();
+  bool have_next = false;                                  // s_next[warp] holds this warp's first tile of phase p
   for (int p = 0; p < a.nphases; ++p) {
-    const int4 ph4 = __ldg(reinterpret_cast<const int4*>(a.phases + p));
-    const int64_t tile_off = __ldg(&a.phases[p].tile_off);
-    const int dir = ph4.x, ws = ph4.y, ntiles = ph4.z;
-    const int tpc = SOLVE_WARPS / ws;
-    const int sub = warp / ws, slice = warp - sub * ws;
-    const int nct = (ntiles + tpc - 1) / tpc;
-    for (int ct = blockIdx.x; ct < nct; ct += gridDim.x) {
-      const int te = ct * tpc + sub;
-      const bool have = te < ntiles;
-      double acc[KT];
-#pragma unroll
-      for (int r = 0; r < KT; ++r) acc[r] = 0.0;
-      TileRec tr;
-      tr.first = tr.nc = tr.nb = tr.tile = 0;
-      tr.soff = tr.w_off = tr.row_off = 0;
-      int out = 0;          // this lane's output index inside the front
-      if (have) {
-        tr = load_tile(a.tiles + tile_off + te);
-        const int nc = tr.nc, f = tr.nc + tr.nb;
-        const int o0 = tr.tile * SOLVE_TILE;
-        out = o0 + lane;
-        if (dir == 0) {
-          // ---- forward: outputs are front rows; acc = S[row, 0:cend) w1 (+ gathered updates of the row)
-          if (slice == 0 && out >= nc && out < f) pull_add<KT>(a, tr.w_off + out, acc);
-          const int cend = min(nc, o0 + SOLVE_TILE);          // S is lower triangular inside the pivot rows
-          const int per = (cend + ws - 1) / ws;
-          const int c0 = slice * per, c1 = min(cend, c0 + per);
-          const double* M = a.sfwd + tr.soff + min(out, f - 1);
-          warp_panel_product<KT>(M, f, c0, c1, lane, stage, acc, [&](int c, double* v) {
-            const int64_t po = __ldg(&a.perm[tr.first + c]);
-            const double* bp = a.B + po * a.brs;
-#pragma unroll
-            for (int r = 0; r < KT; ++r)
-              if (r < k) v[r] = bp[(int64_t)r * a.bcs];
-            pull_add<KT>(a, tr.w_off + c, v);
-          });
-        } else {
-          // ---- backward: outputs are pivot columns; acc = S^T[col, o0:f) [z1 ; x2]
-          const int len = f - o0;
-          const int per = (len + ws - 1) / ws;
-          const int i0 = o0 + slice * per, i1 = min(f, i0 + per);
-          const double* M = a.sbwd + tr.soff + min(out, nc - 1);
-          warp_panel_product<KT>(M, nc, i0, i1, lane, stage, acc, [&](int i, double* v) {
-            if (i < nc) add_row<KT>(a.ybuf, tr.first + i, k, v);
-            else add_row<KT>(a.xperm, __ldg(&a.sn_rows[tr.row_off + i - nc]), k, v);
-          });
+    const PhaseRec ph = p < MAX_PHASES_SMEM ? s_phase[p] : a.phases[p];
+    const int64_t tile_off = ph.tile_off;
+    const int dir = ph.dir, ws = ph.ws, ntiles = ph.ntiles;
+    const bool use_perm = (p == 0);
+    // request this warp's first tile record of the NEXT phase now (static schedule): the load completes
+    // behind this phase's work instead of in front of the next phase's
+    bool nxt_have = false;
+    int4 nxt = make_int4(0, 0, 0, 0);
+    if (p + 1 < a.nphases) {
+      const PhaseRec nx = (p + 1) < MAX_PHASES_SMEM ? s_phase[p + 1] : a.phases[p + 1];
+      if (nx.ws > 0) {
+        const int te = (int)blockIdx.x * (SOLVE_WARPS / nx.ws) + warp / nx.ws;
+        if (te < nx.ntiles) {
+          nxt_have = true;
+          if (lane < 3) nxt = __ldg(reinterpret_cast<const int4*>(a.tiles + nx.tile_off + te) + lane);
         }
       }
-      if (ws > 1) {
-#pragma unroll
-        for (int r = 0; r < KT; ++r) part[(warp * KT + r) * 32 + lane] = acc[r];
-        __syncthreads();
-        if (have && slice == 0)
-          for (int s = 1; s < ws; ++s)
-#pragma unroll
-            for (int r = 0; r < KT; ++r) acc[r] += part[((warp + s) * KT + r) * 32 + lane];
-      }
-      if (have && slice == 0) {
-        const int nc = tr.nc, f = tr.nc + tr.nb;
-        if (dir == 0) {
-          if (out < nc) {
-            const double di = __ldg(&a.dinv[tr.first + out]);
-            double* y = a.ybuf + (int64_t)(tr.first + out) * k;
-#pragma unroll
-            for (int r = 0; r < KT; ++r)
-              if (r < k) y[r] = di * acc[r];
-          } else if (out < f) {
-            double* w = a.wbuf + (tr.w_off + out) * k;
-#pragma unroll
-            for (int r = 0; r < KT; ++r)
-              if (r < k) w[r] = acc[r];
-          }
-        } else if (out < nc) {
-          double* xp = a.xperm + (int64_t)(tr.first + out) * k;
-          double* xo = a.X + (int64_t)__ldg(&a.perm[tr.first + out]) * a.xrs;
-#pragma unroll
-          for (int r = 0; r < KT; ++r)
-            if (r < k) { xp[r] = acc[r]; xo[(int64_t)r * a.xcs] = acc[r]; }
-        }
-      }
-      if (ws > 1) __syncthreads();
     }
+    if (p == 0 && a.nphases > 1) {
+      // permuted copy of the right-hand side for the later phases (coalesced writes, gathered reads)
+      const int k = a.k;
+      for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < (int64_t)a.n * k; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = e / k;
+        const int r = (int)(e - i * k);
+        a.bperm[e] = a.B[(int64_t)__ldg(&a.perm[i]) * a.brs + (int64_t)r * a.bcs];
+      }
+    }
+    if (ws == 0) {
+      // ---- subtree phase: every slot walks the local levels of its own subtrees; only CTA barriers
+      const int nl = ntiles, nslots = ph.level;
+      for (int slot = blockIdx.x; slot < nslots; slot += gridDim.x) {
+        const int* tab = a.sub_ptr + tile_off + (int64_t)slot * (nl + 1);
+        for (int ll = 0; ll < nl; ++ll) {
+          const int l = dir == 0 ? ll : nl - 1 - ll;
+          const int t0 = __ldg(&tab[l]), t1 = __ldg(&tab[l + 1]);
+          for (int te = t0 + warp; te < t1; te += SOLVE_WARPS) {
+            const TileRec tr = load_tile(a.tiles + te);
+            double acc[KT];
+#pragma unroll
+            for (int r = 0; r < KT; ++r) acc[r] = 0.0;
+            tile_compute<KT>(a, dir, use_perm, tr, lane, 0, 1, stage, acc);
+            tile_store<KT>(a, dir, tr, lane, acc);
+          }
+          __syncthreads();      // CTA-scope ordering: the level's results are visible to the whole slot
+        }
+      }
+    } else {
+      const int tpc = SOLVE_WARPS / ws;
+      const int sub = warp / ws, slice = warp - sub * ws;
+      const int nct = (ntiles + tpc - 1) / tpc;
+      for (int ct = blockIdx.x; ct < nct; ct += gridDim.x) {
+        const int te = ct * tpc + sub;
+        const bool have = te < ntiles;
+        double acc[KT];
+#pragma unroll
+        for (int r = 0; r < KT; ++r) acc[r] = 0.0;
+        TileRec tr;
+        tr.first = tr.nc = tr.nb = tr.tile = 0;
+        tr.soff = tr.w_off = tr.row_off = tr.link = 0;
+        if (have) {
+          if (have_next && ct == (int)blockIdx.x) tr = unpack_tile(s_next[warp][0], s_next[warp][1], s_next[warp][2]);
+          else tr = load_tile(a.tiles + tile_off + te);
+          tile_compute<KT>(a, dir, use_perm, tr, lane, slice, ws, stage, acc);
+        }
+        if (ws > 1) {
+#pragma unroll
+          for (int r = 0; r < KT; ++r) part[(warp * KT + r) * 32 + lane] = acc[r];
+          __syncthreads();
+          if (have && slice == 0)
+            for (int s = 1; s < ws; ++s)
+#pragma unroll
+              for (int r = 0; r < KT; ++r) acc[r] += part[((warp + s) * KT + r) * 32 + lane];
+        }
+        if (have && slice == 0) tile_store<KT>(a, dir, tr, lane, acc);
+        if (ws > 1) __syncthreads();
+      }
+    }
+    // ---- hand the prefetched first tile record of the next phase to the whole warp
+    have_next = nxt_have;
+    if (nxt_have && lane < 3) s_next[warp][lane] = nxt;
+    __syncwarp();
     target += gridDim.x;
-    grid_barrier(a.barrier, target);
+    if (p + 1 < a.nphases) grid_barrier(a.barrier, target);
+    if (a.times && blockIdx.x == 0 && threadIdx.x == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+      a.times[p + 1] = t;
+    }
   }
 }
 
@@ -248,7 +376,7 @@ int configure(int slot) {
   int occ = 0;
   EIGD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, solve_kernel<KT>, SOLVE_WARPS * 32, c.smem));
   if (occ < 1) { eigd_set_error("solve: kernel does not fit on an SM"); return 5; }
-  c.grid = g_num_sms * std::min(occ, 2);
+  c.grid = g_num_sms;
   c.ready = true;
   return 0;
 }
@@ -264,7 +392,7 @@ int launch_solve(int slot, eigd_factor* f, SolveArgs& a) {
   EIGD_CUDA(cudaLaunchCooperativeKernel((void*)solve_kernel<KT>, dim3(c.grid), dim3(SOLVE_WARPS * 32), params, c.smem,
                                         g_eigd_stream));
   ++g_eigd_launches;
-  f->bar_base += (unsigned long long)a.nphases * (unsigned long long)c.grid;
+  f->bar_base += (unsigned long long)(a.nphases - 1) * (unsigned long long)c.grid;
   return 0;
 }
 
@@ -277,21 +405,25 @@ int build_solve_plan_dev(eigd_symbolic* S, SymDevHolder* h) {
     EIGD_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   SolvePlanHost P;
-  build_solve_plan_host(S, g_num_sms * 2 * SOLVE_WARPS, P);
+  build_solve_plan_host(S, g_num_sms * SOLVE_WARPS, g_num_sms, -2, P);
   SolvePlanDev& d = h->solve;
   int rc = 0;
   rc |= upload_vec(h, P.tiles, &d.tiles);
   rc |= upload_vec(h, P.phases, &d.phases);
-  std::vector<int2> p2(P.pull2.size() / 2);
-  for (size_t i = 0; i < p2.size(); ++i) p2[i] = make_int2(P.pull2[2 * i], P.pull2[2 * i + 1]);
-  rc |= upload_vec(h, p2, &d.pull2);
+  rc |= upload_vec(h, P.ovf_row, &d.ovf_row);
   rc |= upload_vec(h, P.ovf, &d.ovf);
+  rc |= upload_vec(h, P.sub_ptr, &d.sub_ptr);
   d.nphases = (int)P.phases.size();
   d.host_phases = P.phases;
   return rc;
 }
 
 void free_solve_plan_dev(SymDevHolder*) {}   // the arrays are owned by SymDevHolder::allocs
+
+// developer profiling hook: device buffer of (nphases + 1) u64 receiving per-phase timestamps of the next solves
+static unsigned long long* g_phase_times = nullptr;
+extern "C" int eigd_solve_set_phase_times(void* d_buf) { g_phase_times = (unsigned long long*)d_buf; return 0; }
+extern "C" int eigd_solve_num_phases(const eigd_factor* f) { return f->h->solve.nphases; }
 
 extern "C" int eigd_factor_solve(eigd_factor* f, const double* B, int64_t brs, int64_t bcs, double* X, int64_t xrs,
                                  int64_t xcs, int k) {
@@ -307,10 +439,16 @@ extern "C" int eigd_factor_solve(eigd_factor* f, const double* B, int64_t brs, i
     a.tiles = h->solve.tiles;
     a.phases = h->solve.phases;
     a.nphases = h->solve.nphases;
-    a.pull2 = h->solve.pull2;
+    a.ovf_row = h->solve.ovf_row;
     a.ovf = h->solve.ovf;
+    a.sub_ptr = h->solve.sub_ptr;
     a.perm = h->d.perm;
     a.sn_rows = h->d.sn_rows;
+    a.rel = h->d.rel;
+    a.sumf = f->sym->w_off[f->sym->nsuper];
+    a.slab_stride = a.sumf * kmax;
+    a.bperm = f->bperm;
+    a.n = f->sym->n;
     a.sfwd = f->sfwd;
     a.sbwd = f->sbwd;
     a.dinv = f->dinv;
@@ -324,6 +462,7 @@ extern "C" int eigd_factor_solve(eigd_factor* f, const double* B, int64_t brs, i
     a.xrs = xrs;
     a.xcs = xcs;
     a.k = kc;
+    a.times = g_phase_times;
     int rc;
     if (kc == 1) rc = launch_solve<1>(0, f, a);
     else if (kc == 2) rc = launch_solve<2>(1, f, a);

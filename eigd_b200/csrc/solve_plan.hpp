@@ -10,37 +10,60 @@
 constexpr int SOLVE_WARPS = 16;   // warps per CTA of the solve kernel
 constexpr int SOLVE_TILE = 32;    // outputs (front rows / pivot columns) per warp tile
 
+// link word of a tile record: where the front's update rows go in the forward sweep
+//   bits  0..47  w-row offset of the PARENT front (prefix sum of front sizes)
+//   bits 48..55  slab: 0 / 1 = rank of the front among its siblings (the parent adds slab 0 + slab 1,
+//                no index look-up), 2 = third or later child (own rows in slab 2, the parent
+//                gathers them through the overflow lists), 255 = root (nothing to pass up)
+//   bit  56      the front has children of slab 2 (its rows consult ovf_row)
+//   bit  57      the front has children at all (leaves skip the slab reads)
+constexpr int LINK_SLAB_SHIFT = 48;
+constexpr int64_t LINK_WOFF_MASK = ((int64_t)1 << 48) - 1;
+constexpr int64_t LINK_HAS_OVF = (int64_t)1 << 56;
+constexpr int64_t LINK_HAS_CHILDREN = (int64_t)1 << 57;
+
 // One warp tile: 32 consecutive outputs of one front.  Everything the warp needs about the front
-// travels in this one 48-byte record, so the dependent-load chain per tile is
-// record -> {perm, pull2, rows} -> {b, w, x} instead of five chained index look-ups.
+// travels in this one 48-byte record; the forward sweep needs no further index look-up before it
+// can read its operands (permuted right-hand side and the two child slabs are addressed by the
+// front's own offsets).
 struct TileRec {
   int first, nc, nb, tile;        // first pivot column (permuted), #pivot columns, #rows below, tile index
   int64_t soff;                   // offset of the front's f x nc solve panel (same in S and S^T storage)
   int64_t w_off;                  // offset of the front in the w-row space (prefix sum of front sizes)
-  int64_t row_off;                // offset of the front's below-row list in sn_rows
-  int64_t pad;
+  int64_t row_off;                // offset of the front's below-row list in sn_rows / rel
+  int64_t link;                   // see LINK_*
 };
 static_assert(sizeof(TileRec) == 48, "TileRec is read as three 16-byte words");
 
 // One phase = the tiles of one level of the assembly tree in one direction; phases are separated
 // by a grid-wide barrier.  ws warps share a tile (they split its reduction dimension).
+// ws == 0 marks a SUBTREE phase: the bottom levels 0..cut of the tree are partitioned into complete
+// subtrees, every subtree is owned by one CTA slot, and the slot walks its levels with CTA-local
+// barriers only (no grid barrier below the cut).  For such a phase ntiles = cut + 1 (local levels),
+// level = number of slots and tile_off = offset into SolvePlanHost::sub_ptr of the slot x level table.
 struct PhaseRec {
   int dir, ws, ntiles, level;     // dir 0 forward, 1 backward
   int64_t tile_off;
-  int64_t pad;
+  int64_t pad;                    // tile height (= SOLVE_TILE)
 };
 static_assert(sizeof(PhaseRec) == 32, "PhaseRec layout");
 
 struct SolvePlanHost {
   std::vector<int64_t> soff;      // nsuper + 1, prefix sum of f * nc
-  // deterministic gather form of the multifrontal extend-add of the forward sweep: row t of front p
-  // receives w[pull2[2t]] + w[pull2[2t+1]] (-1 = none); if pull2[2t+1] <= -2 the remaining sources
-  // are ovf[o+1 .. o+1+ovf[o]) with o = -2 - pull2[2t+1]
-  std::vector<int> pull2;         // 2 * sum_front
+  // overflow form of the extend-add of the forward sweep (fronts with more than two children):
+  // ovf_row[t] = -1, or the offset o of a list ovf[o] = count, ovf[o+1 ..] = source rows in slab 2
+  std::vector<int> ovf_row;       // sum_front
   std::vector<int> ovf;
+  std::vector<int> slab;          // per supernode: 0, 1, 2 or 255 (root)
   std::vector<TileRec> tiles;
   std::vector<PhaseRec> phases;   // forward phases (leaves -> root) then backward phases (root -> leaves)
   int nfwd = 0;
+  int cut_level = -1;             // levels <= cut_level are executed by the subtree phases (-1: none)
+  int nslots = 0;
+  std::vector<int> sub_ptr;       // two tables (forward, backward) of nslots * (cut_level + 2) tile indices
+  std::vector<int> sub_slot;      // owning slot of every supernode below the cut (-1 above it)
 };
 
-void build_solve_plan_host(const eigd_symbolic* S, int target_warps, SolvePlanHost& P);
+// target_warps: resident warps the level phases are balanced for; nslots: CTA slots of the subtree
+// phases (0 disables them); cut: -2 = choose automatically, -1 = no subtree phases, >= 0 = forced
+void build_solve_plan_host(const eigd_symbolic* S, int target_warps, int nslots, int cut, SolvePlanHost& P);

@@ -94,10 +94,16 @@ int eigd_symbolic_assembly_map_host(const eigd_symbolic* s, int n, const int* in
 int eigd_symbolic_assembly_map_device(eigd_symbolic* s, int n, const int* d_indptr, const int* d_indices, int64_t* d_map);
 
 /* inspection of the host-built plan of the persistent solve kernel (tests): which = 0 soff[nsuper+1],
- * 1 pull2[2*sum_front], 2 overflow list, 3 tile records (7 values each: first, nc, nb, tile, soff,
- * w_off, row_off), 4 phases (5 values each: dir, ws, ntiles, level, tile_off).  target_warps = resident
- * warps the plan is balanced for.  Returns the element count; copies min(count, cap) values. */
-int64_t eigd_solve_plan_get(const eigd_symbolic* s, int target_warps, int which, int64_t* out, int64_t cap);
+ * 1 ovf_row[sum_front] (-1 or offset into the overflow list), 2 overflow list (count, sources...),
+ * 3 tile records (8 values each: first, nc, nb, tile, soff, w_off, row_off, link), 4 phases (5 values
+ * each: dir, ws, ntiles, level, tile_off; ws == 0 marks a subtree phase), 5 subtree tables (slot x local
+ * level -> first tile), 6 owning slot of every supernode (-1 above the cut), 7 {cut_level, nslots, nfwd},
+ * 8 child slab of every supernode (0, 1, 2 = overflow, 255 = root).
+ * target_warps = resident warps the level phases are balanced for, nslots = CTA slots of the subtree
+ * phases, cut = -2 automatic / -1 no subtree phases / >= 0 forced cut level.
+ * Returns the element count; copies min(count, cap) values. */
+int64_t eigd_solve_plan_get(const eigd_symbolic* s, int target_warps, int nslots, int cut, int which, int64_t* out,
+                            int64_t cap);
 
 int eigd_factor_create(eigd_symbolic* s, int max_rhs, eigd_factor** out);
 /* same, with every device array carved out of a caller-owned buffer of eigd_factor_workspace_bytes()
@@ -112,6 +118,10 @@ int eigd_factor_info(eigd_factor* f, int64_t* info3);
 /* X = (L D L^T)^{-1} B in the original ordering; k columns, (rs, cs) strides; X may alias B */
 int eigd_factor_solve(eigd_factor* f, const double* d_B, int64_t brs, int64_t bcs,
                       double* d_X, int64_t xrs, int64_t xcs, int k);
+/* developer profiling of the persistent solve kernel: d_buf (device, (nphases + 1) x uint64) receives the
+ * %globaltimer of CTA 0 at kernel start and after every phase of the following solves; NULL switches it off */
+int eigd_solve_set_phase_times(void* d_buf);
+int eigd_solve_num_phases(const eigd_factor* f);
 int64_t eigd_factor_bytes(const eigd_factor* f);
 
 /* ---- element kernels: replaces the numpy einsum callbacks and assembly in
