@@ -47,6 +47,10 @@ def parse():
     ap.add_argument("--modes", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-API leg")
+    ap.add_argument("--shard", default="designs", choices=["designs", "modes"],
+                    help="N > 1: 'designs' = one independent design per GPU (weak scaling, no data-path collective); "
+                         "'modes' = one design, per-mode adjoint solves and df/dx element ranges sharded (strong scaling)")
+    ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the extra strong-scaling measurement")
     return ap.parse_args()
 
 
@@ -128,15 +132,20 @@ def run_reference(args, rank):
 
 def base_line(args, value, ms):
     n = (args.nx + 1) ** 2
+    weak = args.gpus > 1 and args.shard == "designs"
     return {"metric": "time_to_gradient", "value": value, "unit": "s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False, "scaling": "strong",
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False, "scaling": "weak" if weak else "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "thermal_q4_nx%d_ny%d_%ddof_N%d_m%d_iram_sibk" % (args.nx, args.nx, n, args.modes, MLANCZOS),
                        "baseline_config": "configs[1]: examples/thermal.py scaled to ~250k DOF, 10 modes, single B200",
                        "sigma": SIGMA, "rtol": 1e-10, "deriv_type": "tensor",
                        "l2": "explicit 256 MiB L2 flush between timed steps; per-step working set ~1 GB > 126 MB L2",
                        "parallelism": "1 GPU" if args.gpus == 1 else
-                       "eigensolve replicated, per-mode adjoint + element-range dfdx sharded over %d GPUs" % args.gpus}}
+                       ("design-batch sweep (BASELINE configs[4] pattern): %d independent designs of the same mesh, one per "
+                        "GPU, no data-path collective; value = step time (max over ranks) / %d designs" % (args.gpus, args.gpus)
+                        if weak else
+                        "one design: eigensolve replicated, per-mode adjoint + element-range dfdx sharded over %d GPUs"
+                        % args.gpus)}}
 
 
 # ------------------------------------------------------------------------------------------
@@ -194,7 +203,8 @@ def run_ours(args, rank, world):
     torch.cuda.set_device(local)
     D.init("cuda:%d" % local)
     shard = None
-    if world > 1:
+    designs = world > 1 and args.shard == "designs"
+    if world > 1 and not designs:
         from eigd_b200.dist import ModeSharding
         shard = ModeSharding()
     N = args.modes
@@ -202,9 +212,9 @@ def run_ours(args, rank, world):
                                  adjoint_method="sibk", adjoint_options={"lanczos_guess": True}, rtol=1e-10,
                                  deriv_type="tensor", seed=0)
     model.sharding = shard
-    rng = np.random.default_rng(0)
+    rng = np.random.default_rng(rank if designs else 0)     # designs mode: rank r evaluates design r
     x_h = rng.uniform(0.3, 1.0, model.nnodes)
-    vec_h = rng.uniform(size=model.nnodes)
+    vec_h = np.random.default_rng(12345).uniform(size=model.nnodes)
     x_d, vec_d = D.to_device(x_h), D.to_device(vec_h)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
@@ -261,6 +271,43 @@ def run_ours(args, rank, world):
     tl = D.Timeline.summary()
     per_step_ms = [a.elapsed_time(b) for a, b in evs]
     ms = sum(per_step_ms) / args.steps
+    # ---- N > 1, designs mode: also time ONE design with the sharded stages (strong scaling) -----------
+    strong = None
+    if designs and not args.no_strong:
+        from eigd_b200.dist import ModeSharding
+        sh = ModeSharding()
+        x0_d = D.to_device(np.random.default_rng(0).uniform(0.3, 1.0, model.nnodes))   # same design on every rank
+        model.sharding = sh
+
+        def step_strong():
+            model.initialize(x=x0_d)
+            model.initialize_adjoint()
+            model.add_thermal_compliance_derivative(1.0, vec_d)
+            model.finalize_adjoint()
+
+        for _ in range(2):
+            step_strong()
+        tms = []
+        stage_s = {"eigenvalue solve time": 0.0, "adjoint solution time": 0.0, "total derivative time": 0.0}
+        for _ in range(args.steps):
+            flush.fill_(1)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            step_strong()
+            e1.record()
+            torch.cuda.synchronize()
+            tms.append(e0.elapsed_time(e1))
+            for k in stage_s:
+                stage_s[k] += model.profile[k] / args.steps
+        barrier()
+        t = torch.tensor([sum(tms) / len(tms)] + [stage_s[k] for k in sorted(stage_s)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        strong = {"value": float(t[0]) / 1e3, "unit": "s", "scaling": "strong",
+                  "parallelism": "one design: eigensolve + factorisation replicated, per-mode adjoint solves (mode i -> "
+                                 "rank i mod N, one all-gather) and df/dx element ranges (one all-gather) sharded",
+                  "stages_s_max_over_ranks": {k: float(v) for k, v in zip(sorted(stage_s), t[1:].tolist())}}
+        model.sharding = None
     # ---- end to end through the numpy API (host CSR in, host df/dx out) ---------------------------
     K_h, M_h = model.K.to_scipy(), model.M.to_scipy()
     prob = model.prob
@@ -300,6 +347,7 @@ def run_ours(args, rank, world):
         t = torch.tensor([ms, e2e_s or 0.0], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, e2e_s = float(t[0]), float(t[1])
+    units = world if designs else 1          # gradients produced per step by the whole job
     if rank != 0:
         return
     peaks = {}
@@ -310,10 +358,13 @@ def run_ours(args, rank, world):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     sol = tl.get("solve", {"calls": 0, "ms": 0.0, "bytes": 0.0, "launches": 0})
     achieved = (sol["bytes"] / 1e9) / (sol["ms"] / 1e3) if sol["ms"] > 0 else 0.0
-    line = base_line(args, ms / 1e3, ms)
+    line = base_line(args, ms / 1e3 / units, ms)
+    if strong is not None:
+        line["strong_single_gradient"] = strong
     line.update({
         "impl": "ours", "gpu_launches": int(launches // max(args.steps, 1)), "clocks": clk,
-        "e2e": {"value": e2e_s, "unit": "s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+        "e2e": {"value": (e2e_s / units) if e2e_s else e2e_s, "unit": "s", "h2d_bytes_per_step": int(h2d) * units,
+                "d2h_bytes_per_step": int(d2h) * units,
                 "note": "numpy API: scipy CSR K, M, K - sigma M uploaded from pageable host memory; Phi, psi, dfdx read back"},
         "stages_s": stage, "per_step_ms": per_step_ms,
         "roofline": {"bound": "hbm", "kernel": "multifrontal LDL^T triangular solve (forward+backward sweep = one eigd_factor_solve call)",
