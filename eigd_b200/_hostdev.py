@@ -31,8 +31,9 @@ def as_csr_device(A):
     if base is not None and hasattr(base, "tocsr"):
         A = base
     if hasattr(A, "tocsr"):
-        XFER["h2d"] += A.nnz * 12 + (A.shape[0] + 1) * 4
-        return D.CsrDevice.from_scipy(A)
+        out = D.CsrDevice.from_scipy(A)
+        XFER["h2d"] += out.uploaded_bytes
+        return out
     raise TypeError("eigd_b200 needs a scipy sparse matrix or a device.CsrDevice, got %r (there is no "
                     "dense / LinearOperator CPU fallback)" % type(A))
 

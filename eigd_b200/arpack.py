@@ -220,7 +220,6 @@ def eigsh_mod(A, k=6, M=None, sigma=None, which="LM", v0=None, ncv=None, maxiter
     st = lanczos_thick_restart(Bip, OPinv, k, ncv, float(sigma), mode=mode, tol=float(tol), maxiter=maxiter, v0=v0, seed=seed)
     if not return_eigenvectors:
         return st.d
-    out = (st.d, to_host(st.Z), st.T, to_host(st.Vt).T.copy() if not return_state else None)
-    if return_state:
-        return out + (st,)
-    return out
+    if return_state:                  # the caller keeps the basis and the eigenvectors in HBM (IRAM.solve)
+        return (st.d, None, st.T, None, st)
+    return (st.d, to_host(st.Z), st.T, to_host(st.Vt).T.copy())

@@ -149,17 +149,29 @@ class CsrDevice:
         self.dtype = np.dtype(np.float64)
 
     @classmethod
-    def from_scipy(cls, A):
+    def from_scipy(cls, A, symmetric=False):
+        """scipy sparse -> device CSR.  The int32 structure goes through PatternCache (uploaded once per
+        pattern).  symmetric=True: a CSC matrix is taken as the CSR of its transpose (= itself)."""
         import scipy.sparse as sp
-        A = sp.csr_matrix(A)
+        if not (sp.issparse(A) and (A.format == "csr" or (symmetric and A.format == "csc"))):
+            A = sp.csr_matrix(A)
         if not A.has_sorted_indices:
             A = A.sorted_indices()
-        return cls(A.indptr, A.indices, A.data, A.shape)
+        indptr = np.ascontiguousarray(A.indptr, dtype=np.int32)
+        indices = np.ascontiguousarray(A.indices, dtype=np.int32)
+        eid, ip_d, ix_d, fresh = PatternCache.get(indptr, indices)
+        out = cls(ip_d, ix_d, A.data, A.shape)
+        out.pattern_id = eid
+        out.pattern_host = (indptr, indices)
+        out.uploaded_bytes = A.nnz * 8 + ((A.nnz * 4 + (A.shape[0] + 1) * 4) if fresh else 0)
+        return out
 
     def with_values(self, data):
         out = object.__new__(CsrDevice)
         out.shape, out.indptr, out.indices, out.nnz, out.dtype = self.shape, self.indptr, self.indices, self.nnz, self.dtype
         out.data = _chk(data, "values")
+        out.pattern_id = getattr(self, "pattern_id", None)
+        out.pattern_host = getattr(self, "pattern_host", None)
         return out
 
     def spmm(self, X, out=None, alpha=1.0, beta=0.0):
@@ -352,6 +364,36 @@ def pattern_key(indptr, indices, extra=b""):
     h.update(np.ascontiguousarray(indices).view(np.uint8))
     h.update(extra)
     return h.hexdigest()
+
+
+class PatternCache:
+    """Device copies of CSR structures (indptr, indices), shared by every matrix with that pattern.
+
+    K, M and K - sigma*M of one design -- and of every later design on the same mesh -- have identical
+    patterns (examples/natural_frequency.py:94-104,157,233), so the int32 structure is uploaded once and
+    only the fp64 values travel per matrix.  Look-up: a cheap fingerprint (sizes + strided sums) selects
+    the candidate, a full array comparison against the cached host copy confirms it."""
+    _entries = {}
+
+    @staticmethod
+    def _fingerprint(indptr, indices):
+        return (len(indptr), len(indices), int(indptr[::61].sum()), int(indices[::127].sum()),
+                int(indices[: 64].sum()), int(indices[-64:].sum()))
+
+    @classmethod
+    def get(cls, indptr, indices):
+        """-> (entry id, device indptr, device indices); arrays must be int32, contiguous, sorted rows."""
+        fp = cls._fingerprint(indptr, indices)
+        for ent in cls._entries.get(fp, []):
+            if np.array_equal(ent[1], indptr) and np.array_equal(ent[2], indices):
+                return ent[0], ent[3], ent[4], False
+        d = dev()
+        if sum(len(v) for v in cls._entries.values()) > 16:
+            cls._entries.clear()
+        eid = "p%d_%d_%d" % (fp[0], fp[1], id(indices))
+        ent = (eid, indptr.copy(), indices.copy(), torch.as_tensor(indptr, device=d), torch.as_tensor(indices, device=d))
+        cls._entries.setdefault(fp, []).append(ent)
+        return eid, ent[3], ent[4], True
 
 
 class Factor:

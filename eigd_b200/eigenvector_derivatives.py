@@ -56,21 +56,13 @@ class SpLuOperator:
     def __init__(self, mat, coords=None, dof_per_node=1, symbolic=None, refine=None, max_rhs=32):
         if isinstance(mat, D.CsrDevice):
             csr = mat
-            indptr_h = indices_h = None
         else:
             if not hasattr(mat, "tocsr"):
                 raise TypeError("SpLuOperator needs a scipy sparse matrix or a device.CsrDevice")
             if np.iscomplexobj(mat.data):
                 raise NotImplementedError("complex matrices (complex-step) are not supported on the device path")
-            fmt = getattr(mat, "format", None)
-            if fmt not in ("csr", "csc"):          # symmetric: CSC arrays of mat are CSR arrays of mat
-                mat = mat.tocsr()
-            if not mat.has_sorted_indices:
-                mat = mat.sorted_indices()
-            indptr_h = np.ascontiguousarray(mat.indptr, dtype=np.int32)
-            indices_h = np.ascontiguousarray(mat.indices, dtype=np.int32)
-            csr = D.CsrDevice(indptr_h, indices_h, mat.data, mat.shape)
-            XFER["h2d"] += mat.nnz * 12 + (mat.shape[0] + 1) * 4
+            csr = D.CsrDevice.from_scipy(mat, symmetric=True)   # symmetric: CSC arrays of mat are CSR arrays of mat
+            XFER["h2d"] += csr.uploaded_bytes
         if csr.shape[0] != csr.shape[1]:
             raise ValueError("expected square matrix")
         self.shape = csr.shape
@@ -79,13 +71,15 @@ class SpLuOperator:
         self.mat = csr
         n = csr.shape[0]
         if symbolic is None:
-            if indptr_h is None:
-                indptr_h, indices_h = to_host(csr.indptr), to_host(csr.indices)
-            extra = b"geo%d" % dof_per_node if coords is not None else b"graph"
-            key = D.pattern_key(indptr_h, indices_h, extra)
+            extra = "geo%d" % dof_per_node if coords is not None else "graph"
+            pid = getattr(csr, "pattern_id", None)
+            host = getattr(csr, "pattern_host", None)
+            if host is None:
+                host = (to_host(csr.indptr), to_host(csr.indices))
+            key = (pid, extra) if pid is not None else D.pattern_key(host[0], host[1], extra.encode())
             cached = _SYMBOLIC_CACHE.get(key)
             if cached is None:
-                sym = D.Symbolic(indptr_h, indices_h, n, coords=coords, dof_per_node=dof_per_node)
+                sym = D.Symbolic(host[0], host[1], n, coords=coords, dof_per_node=dof_per_node)
                 amap = sym.assembly_map_device(csr.indptr, csr.indices)
                 if len(_SYMBOLIC_CACHE) > 8:
                     _SYMBOLIC_CACHE.clear()
