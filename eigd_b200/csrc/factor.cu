@@ -258,7 +258,12 @@ extend_add_kernel(SymDev d, const int2* __restrict__ tasks, double* __restrict__
   }
 }
 
-// LDL^T of one 32-wide pivot block + inverse of its unit-lower factor; one CTA per front
+// LDL^T of one 32-wide pivot block + inverse of its unit-lower factor; one CTA per front.
+// Threads are (tx = row, ty = column class mod 8).  Right-looking elimination with ONE barrier per
+// column: every thread derives the (possibly perturbed) pivot from the same shared entry, the column is
+// kept unscaled during the elimination and divided by its pivot afterwards.  The inverse of the unit
+// lower triangle is computed column by column by groups of 8 consecutive lanes (shuffle reductions,
+// no block barrier).
 __global__ void __launch_bounds__(256)
 diag_factor_kernel(SymDev d, const int2* __restrict__ tasks, int kb, double* __restrict__ fronts,
                    double* __restrict__ linv, double* __restrict__ dval, double* __restrict__ dinv,
@@ -266,9 +271,7 @@ diag_factor_kernel(SymDev d, const int2* __restrict__ tasks, int kb, double* __r
                    unsigned long long* __restrict__ info) {
   __shared__ double T[NB][NB + 1];
   __shared__ double Li[NB][NB + 1];
-  __shared__ double colj[NB];
-  __shared__ double sh_d;
-  __shared__ int sh_neg, sh_pert, sh_bad;
+  __shared__ double ds[NB];
   int s = tasks[blockIdx.x].x;
   int first = d.sn_first[s];
   int nc = d.sn_first[s + 1] - first;
@@ -276,58 +279,59 @@ diag_factor_kernel(SymDev d, const int2* __restrict__ tasks, int kb, double* __r
   int j0 = kb * NB;
   int bs = min(NB, nc - j0);
   double* F = fronts + d.front_off[s];
-  const int tid = threadIdx.x;
-  if (tid == 0) { sh_neg = 0; sh_pert = 0; sh_bad = 0; }
-  for (int e = tid; e < NB * NB; e += blockDim.x) {
-    int i = e % NB, j = e / NB;
-    T[i][j] = (i < bs && j < bs && i >= j) ? F[(j0 + i) + (int64_t)(j0 + j) * f] : 0.0;
-    Li[i][j] = (i == j) ? 1.0 : 0.0;
+  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  for (int c = ty; c < NB; c += 8) {
+    T[tx][c] = (tx < bs && c < bs && tx >= c) ? F[(j0 + tx) + (int64_t)(j0 + c) * f] : 0.0;
+    Li[tx][c] = (tx == c) ? 1.0 : 0.0;
   }
-  double thr = piv_tol * __longlong_as_double((long long)(*amax_bits));
+  const double thr = piv_tol * __longlong_as_double((long long)(*amax_bits));
+  int nneg = 0, npert = 0, nbad = 0;
   __syncthreads();
   for (int j = 0; j < bs; ++j) {
-    if (tid == 0) {
-      double dj = T[j][j];
-      if (!(dj == dj) || fabs(dj) > 1e300) { sh_bad++; dj = thr > 0.0 ? thr : 1.0; }
-      if (fabs(dj) < thr) { dj = (dj >= 0.0) ? thr : -thr; sh_pert++; }
-      if (dj < 0.0) sh_neg++;
-      T[j][j] = dj;
-      sh_d = dj;
+    double dj = T[j][j];
+    if (!(dj == dj) || fabs(dj) > 1e300) { nbad++; dj = thr > 0.0 ? thr : 1.0; }
+    if (fabs(dj) < thr) { dj = (dj >= 0.0) ? thr : -thr; npert++; }
+    if (dj < 0.0) nneg++;
+    if (tid == 0) ds[j] = dj;
+    const double rd = 1.0 / dj;
+    if (tx > j) {
+      const double lij = T[tx][j] * rd;
+      for (int c = j + 1 + ((ty - (j + 1)) & 7); c <= tx; c += 8) T[tx][c] = fma(-lij, T[c][j], T[tx][c]);
     }
-    if (tid > j && tid < bs) colj[tid] = T[tid][j];
-    __syncthreads();
-    double rd = 1.0 / sh_d;
-    for (int e = tid; e < bs * bs; e += blockDim.x) {
-      int i = e % bs, c = e / bs;
-      if (c > j && i >= c) T[i][c] = fma(-colj[i], colj[c] * rd, T[i][c]);
-    }
-    if (tid > j && tid < bs) T[tid][j] = colj[tid] * rd;
     __syncthreads();
   }
-  // inverse of the unit lower triangle, one column per thread
-  if (tid < bs) {
-    int c = tid;
+  // scale the columns: L(i, j) = T(i, j) / d_j
+  for (int c = ty; c < bs; c += 8)
+    if (tx > c && tx < bs) T[tx][c] *= 1.0 / ds[c];
+  __syncthreads();
+  // inverse of the unit lower triangle: column c by lanes 8c .. 8c+7 of the block (32 columns x 8 lanes)
+  {
+    const int c = tid >> 3, q = tid & 7;
+    const unsigned gmask = 0xffu << (8 * (c & 3));        // the four column groups of a warp run different trip counts
     for (int i = c + 1; i < bs; ++i) {
       double sum = 0.0;
-      for (int k = c; k < i; ++k) sum = fma(T[i][k], Li[k][c], sum);
-      Li[i][c] = -sum;
+      for (int k = c + q; k < i; k += 8) sum = fma(T[i][k], Li[k][c], sum);
+      sum += __shfl_xor_sync(gmask, sum, 1);
+      sum += __shfl_xor_sync(gmask, sum, 2);
+      sum += __shfl_xor_sync(gmask, sum, 4);
+      if (q == 0) Li[i][c] = -sum;
+      __syncwarp(gmask);
     }
   }
   __syncthreads();
-  for (int e = tid; e < bs * bs; e += blockDim.x) {
-    int i = e % bs, j = e / bs;
-    if (i >= j) F[(j0 + i) + (int64_t)(j0 + j) * f] = T[i][j];
-  }
+  for (int c = ty; c < bs; c += 8)
+    if (tx < bs && tx > c) F[(j0 + tx) + (int64_t)(j0 + c) * f] = T[tx][c];
+  if (tid < bs) F[(j0 + tid) + (int64_t)(j0 + tid) * f] = ds[tid];
   double* Lo = linv + d.linv_off[s] + (int64_t)kb * NB * NB;
-  for (int e = tid; e < NB * NB; e += blockDim.x) Lo[e] = Li[e % NB][e / NB];   // column-major: Lo[i + j*NB]
+  for (int c = ty; c < NB; c += 8) Lo[tx + c * NB] = Li[tx][c];   // column-major: Lo[i + j*NB]
   if (tid < bs) {
-    dval[first + j0 + tid] = T[tid][tid];
-    dinv[first + j0 + tid] = 1.0 / T[tid][tid];
+    dval[first + j0 + tid] = ds[tid];
+    dinv[first + j0 + tid] = 1.0 / ds[tid];
   }
   if (tid == 0) {
-    if (sh_neg) atomicAdd(&info[0], (unsigned long long)sh_neg);
-    if (sh_pert) atomicAdd(&info[1], (unsigned long long)sh_pert);
-    if (sh_bad) atomicAdd(&info[2], (unsigned long long)sh_bad);
+    if (nneg) atomicAdd(&info[0], (unsigned long long)nneg);
+    if (npert) atomicAdd(&info[1], (unsigned long long)npert);
+    if (nbad) atomicAdd(&info[2], (unsigned long long)nbad);
   }
 }
 
@@ -363,12 +367,23 @@ trsm_kernel(SymDev d, const int2* __restrict__ tasks, int kb, double* __restrict
   }
 }
 
-// trailing update C(i,c) -= sum_k L(i,k) d_k L(c,k) over one pivot block; 64x64 lower tiles
+// trailing update C(i,c) -= sum_k L(i,k) d_k L(c,k) over one pivot block; 64x64 lower tiles on the FP64
+// tensor pipe (mma.sync.m8n8k4.f64 -> DMMA): 8 warps as 4 row groups x 2 column groups, each warp owns a
+// 16 x 32 block = 2 x 4 MMA tiles, K = 32 in eight k-steps.  Operands are staged in shared memory with a
+// row stride of NB + 4 doubles: the fragment loads (row = lane / 4, k = lane % 4) are then conflict-free.
+constexpr int UPD_LD = NB + 4;
+
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
 __global__ void __launch_bounds__(256)
 trailing_update_kernel(SymDev d, const int2* __restrict__ tasks, int kb, double* __restrict__ fronts,
                        const double* __restrict__ dval) {
-  __shared__ double As[UPD_TILE][NB + 1];
-  __shared__ double Bs[UPD_TILE][NB + 1];
+  __shared__ double As[UPD_TILE][UPD_LD];
+  __shared__ double Bs[UPD_TILE][UPD_LD];
   int2 tk = tasks[blockIdx.x];
   int s = tk.x;
   int ti, tj;
@@ -392,34 +407,39 @@ trailing_update_kernel(SymDev d, const int2* __restrict__ tasks, int kb, double*
     Bs[r][k] = b;
   }
   __syncthreads();
-  int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  double acc[4][4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wr = (warp & 3) * 16, wc = (warp >> 2) * 32;
+  const int fr = lane >> 2, fk = lane & 3;
+  double acc[2][4][2];
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
+  for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
-#pragma unroll 8
-  for (int k = 0; k < NB; ++k) {
-    double av[4], bv[4];
+    for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
 #pragma unroll
-    for (int a = 0; a < 4; ++a) av[a] = As[tx + 16 * a][k];
+  for (int k0 = 0; k0 < NB; k0 += 4) {
+    double a[2], b[4];
 #pragma unroll
-    for (int b = 0; b < 4; ++b) bv[b] = Bs[ty + 16 * b][k];
+    for (int mi = 0; mi < 2; ++mi) a[mi] = As[wr + mi * 8 + fr][k0 + fk];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int ni = 0; ni < 4; ++ni) b[ni] = Bs[wc + ni * 8 + fr][k0 + fk];
 #pragma unroll
-      for (int b = 0; b < 4; ++b) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) dmma_m8n8k4(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
   }
+  // accumulator layout: row = lane / 4, columns 2 * (lane % 4) + {0, 1}
 #pragma unroll
-  for (int b = 0; b < 4; ++b) {
-    int64_t c = cb + ty + 16 * b;
-    if (c >= f) continue;
+  for (int ni = 0; ni < 4; ++ni)
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      int64_t i = ib + tx + 16 * a;
-      if (i < f && i >= c) F[i + c * f] -= acc[a][b];
+    for (int q = 0; q < 2; ++q) {
+      int64_t c = cb + wc + ni * 8 + 2 * fk + q;
+      if (c >= f) continue;
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi) {
+        int64_t i = ib + wr + mi * 8 + fr;
+        if (i < f && i >= c) F[i + c * f] -= acc[mi][ni][q];
+      }
     }
-  }
 }
 
 // ---------------------------------------------------------------------------------------

@@ -115,7 +115,7 @@ __device__ __forceinline__ TileRec load_tile(const TileRec* p) {
 template <int KT, class StageFn>
 __device__ __forceinline__ void warp_panel_product(const double* __restrict__ M, int64_t ld, int c0, int c1, int lane,
                                                    double* stage, double* acc, StageFn stage_fn) {
-  constexpr int MC = KT <= 2 ? 32 : (KT <= 8 ? 16 : 8);
+  constexpr int MC = KT <= 2 ? 32 : (KT <= 10 ? 16 : 8);
   constexpr int g = 0, nks = 1;
   for (int cc = c0; cc < c1; cc += 32) {
     const int ncol = min(32, c1 - cc);
@@ -364,7 +364,7 @@ struct KernelCfg {
   int grid = 0;
   size_t smem = 0;
 };
-KernelCfg g_cfg[5];
+KernelCfg g_cfg[8];
 int g_num_sms = 0;
 
 template <int KT>
@@ -467,8 +467,11 @@ extern "C" int eigd_factor_solve(eigd_factor* f, const double* B, int64_t brs, i
     if (kc == 1) rc = launch_solve<1>(0, f, a);
     else if (kc == 2) rc = launch_solve<2>(1, f, a);
     else if (kc <= 4) rc = launch_solve<4>(2, f, a);
-    else if (kc <= 8) rc = launch_solve<8>(3, f, a);
-    else rc = launch_solve<16>(4, f, a);
+    else if (kc <= 6) rc = launch_solve<6>(3, f, a);
+    else if (kc <= 8) rc = launch_solve<8>(4, f, a);
+    else if (kc <= 10) rc = launch_solve<10>(5, f, a);
+    else if (kc <= 12) rc = launch_solve<12>(6, f, a);
+    else rc = launch_solve<16>(7, f, a);
     if (rc) return rc;
   }
   return 0;
