@@ -45,8 +45,12 @@ SIGNATURES = {
     "eigd_factor_info": (c_int, [c_ptr, c_ptr]),
     "eigd_factor_solve": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_i64, c_i64, c_int]),
     "eigd_factor_bytes": (c_i64, [c_ptr]),
+    "eigd_solve_timing_begin": (c_int, []),
+    "eigd_solve_timing_end": (c_int, [c_ptr, c_ptr]),
     "eigd_solve_set_phase_times": (c_int, [c_ptr]),
     "eigd_solve_num_phases": (c_int, [c_ptr]),
+    "eigd_lanczos_extend": (c_int, [c_ptr, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_int,
+                                    c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_ptr]),
     "eigd_q4_assemble": (c_int, [c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_ptr]),
     "eigd_q4_quadforms": (c_int, [c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_ptr, c_ptr, c_dbl, c_dbl, c_ptr]),
     "eigd_q4_material": (c_int, [c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),

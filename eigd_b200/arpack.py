@@ -98,23 +98,9 @@ def lanczos_thick_restart(Bip, factor, k, ncv, sigma, mode="normal", tol=0.0, ma
     best = np.inf
     stagnant = 0
     while True:
-        for j in range(j0, ncv):
-            factor.solve_dev(BVt[j], out=w)
-            st.nops += 1
-            Vj, BVj = Vt[: j + 1].T, BVt[: j + 1].T          # logical (n, j+1), vector-major strides
-            h = hbuf[: j + 1]
-            g = h2[: j + 1]
-            D.gemm_tn(BVj, w, out=h.unsqueeze(1))
-            D.gemm_nn(Vj, h.unsqueeze(1), w, alpha=-1.0, beta=1.0)
-            D.gemm_tn(BVj, w, out=g.unsqueeze(1))            # second pass (DGKS)
-            D.gemm_nn(Vj, g.unsqueeze(1), w, alpha=-1.0, beta=1.0)
-            # alpha_j = h[j] + g[j]
-            D.axpby(1.0, h[j: j + 1], 1.0, g[j: j + 1], out=ab[0, j: j + 1])
-            Bip.spmm(w, out=BVt[j + 1])
-            D.col_dot(w, BVt[j + 1], out=ab[1, j: j + 1])
-            Vt[j + 1].copy_(w)
-            D.col_scale(Vt[j + 1], ab[1, j: j + 1], mode=2)
-            D.col_scale(BVt[j + 1], ab[1, j: j + 1], mode=2)
+        # steps j0 .. ncv-1 of the recurrence in one native call (csrc/krylov.cu): no host round trip per step
+        D.lanczos_extend(factor, Bip, Vt, BVt, j0, ncv, w, hbuf, h2, ab)
+        st.nops += ncv - j0
         st.ncycles += 1
         abh = to_host(ab)                                    # the one D2H of the cycle
         if not np.all(np.isfinite(abh[:, j0:ncv])) or np.any(abh[1, j0:ncv] <= 0.0):

@@ -252,10 +252,20 @@ extend_add_kernel(SymDev d, const int2* __restrict__ tasks, double* __restrict__
   int i = ti * EA_TILE + tx;
   if (i >= nb) return;
   int ri = rel[i];
-  for (int jj = ty; jj < EA_TILE; jj += 8) {
-    int j = tj * EA_TILE + jj;
-    if (j < nb && j <= i) P[ri + (int64_t)rel[j] * fp] += C[i + (int64_t)j * fc];
+  // loads first, stores afterwards (parent and child live in the same array: see trailing_update_kernel)
+  double pv[EA_TILE / 8], cv[EA_TILE / 8];
+  int64_t pa[EA_TILE / 8];
+#pragma unroll
+  for (int q = 0; q < EA_TILE / 8; ++q) {
+    int j = tj * EA_TILE + ty + 8 * q;
+    bool ok = j < nb && j <= i;
+    pa[q] = ok ? ri + (int64_t)rel[j] * fp : -1;
+    cv[q] = ok ? C[i + (int64_t)j * fc] : 0.0;
+    pv[q] = ok ? P[pa[q]] : 0.0;
   }
+#pragma unroll
+  for (int q = 0; q < EA_TILE / 8; ++q)
+    if (pa[q] >= 0) P[pa[q]] = pv[q] + cv[q];
 }
 
 // LDL^T of one 32-wide pivot block + inverse of its unit-lower factor; one CTA per front.
@@ -427,17 +437,30 @@ trailing_update_kernel(SymDev d, const int2* __restrict__ tasks, int kb, double*
 #pragma unroll
       for (int ni = 0; ni < 4; ++ni) dmma_m8n8k4(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
   }
-  // accumulator layout: row = lane / 4, columns 2 * (lane % 4) + {0, 1}
+  // accumulator layout: row = lane / 4, columns 2 * (lane % 4) + {0, 1}.  All old values are loaded before
+  // the first store: loads and stores go through the same pointer, so a load placed after a store would
+  // have to wait for it (16 serialised DRAM round trips instead of one).
+  double old[2][4][2];
 #pragma unroll
   for (int ni = 0; ni < 4; ++ni)
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
-      int64_t c = cb + wc + ni * 8 + 2 * fk + q;
-      if (c >= f) continue;
+      const int64_t c = cb + wc + ni * 8 + 2 * fk + q;
 #pragma unroll
       for (int mi = 0; mi < 2; ++mi) {
-        int64_t i = ib + wr + mi * 8 + fr;
-        if (i < f && i >= c) F[i + c * f] -= acc[mi][ni][q];
+        const int64_t i = ib + wr + mi * 8 + fr;
+        old[mi][ni][q] = (c < f && i < f && i >= c) ? F[i + c * f] : 0.0;
+      }
+    }
+#pragma unroll
+  for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int64_t c = cb + wc + ni * 8 + 2 * fk + q;
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi) {
+        const int64_t i = ib + wr + mi * 8 + fr;
+        if (c < f && i < f && i >= c) F[i + c * f] = old[mi][ni][q] - acc[mi][ni][q];
       }
     }
 }

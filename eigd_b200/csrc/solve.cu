@@ -23,6 +23,7 @@
 #include "../../include/eigd_b200.h"
 
 #include <algorithm>
+#include <vector>
 
 namespace {
 
@@ -420,6 +421,39 @@ int build_solve_plan_dev(eigd_symbolic* S, SymDevHolder* h) {
 
 void free_solve_plan_dev(SymDevHolder*) {}   // the arrays are owned by SymDevHolder::allocs
 
+// ---- live timing of every solve launch (bench.py roofline): CUDA events on the launching stream ----------
+struct SolveTiming {
+  cudaEvent_t e0, e1;
+  int k;
+};
+static bool g_timing_on = false;
+static std::vector<SolveTiming> g_timings;
+
+extern "C" int eigd_solve_timing_begin(void) {
+  for (auto& t : g_timings) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
+  g_timings.clear();
+  g_timing_on = true;
+  return 0;
+}
+
+// calls_by_k / ms_by_k: 33 entries each (index = number of right-hand sides of the launch, 1 .. 32)
+extern "C" int eigd_solve_timing_end(int64_t* calls_by_k, double* ms_by_k) {
+  g_timing_on = false;
+  for (int i = 0; i < 33; ++i) { calls_by_k[i] = 0; ms_by_k[i] = 0.0; }
+  for (auto& t : g_timings) {
+    EIGD_CUDA(cudaEventSynchronize(t.e1));
+    float ms = 0.f;
+    EIGD_CUDA(cudaEventElapsedTime(&ms, t.e0, t.e1));
+    int k = t.k < 32 ? t.k : 32;
+    calls_by_k[k] += 1;
+    ms_by_k[k] += ms;
+    cudaEventDestroy(t.e0);
+    cudaEventDestroy(t.e1);
+  }
+  g_timings.clear();
+  return 0;
+}
+
 // developer profiling hook: device buffer of (nphases + 1) u64 receiving per-phase timestamps of the next solves
 static unsigned long long* g_phase_times = nullptr;
 extern "C" int eigd_solve_set_phase_times(void* d_buf) { g_phase_times = (unsigned long long*)d_buf; return 0; }
@@ -464,6 +498,13 @@ extern "C" int eigd_factor_solve(eigd_factor* f, const double* B, int64_t brs, i
     a.k = kc;
     a.times = g_phase_times;
     int rc;
+    SolveTiming tm;
+    if (g_timing_on) {
+      tm.k = kc;
+      EIGD_CUDA(cudaEventCreate(&tm.e0));
+      EIGD_CUDA(cudaEventCreate(&tm.e1));
+      EIGD_CUDA(cudaEventRecord(tm.e0, g_eigd_stream));
+    }
     if (kc == 1) rc = launch_solve<1>(0, f, a);
     else if (kc == 2) rc = launch_solve<2>(1, f, a);
     else if (kc <= 4) rc = launch_solve<4>(2, f, a);
@@ -473,6 +514,10 @@ extern "C" int eigd_factor_solve(eigd_factor* f, const double* B, int64_t brs, i
     else if (kc <= 12) rc = launch_solve<12>(6, f, a);
     else rc = launch_solve<16>(7, f, a);
     if (rc) return rc;
+    if (g_timing_on) {
+      EIGD_CUDA(cudaEventRecord(tm.e1, g_eigd_stream));
+      g_timings.push_back(tm);
+    }
   }
   return 0;
 }

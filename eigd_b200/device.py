@@ -97,6 +97,19 @@ def dev():
     return _State.device
 
 
+def solve_timing_begin():
+    check(_lib.load().eigd_solve_timing_begin(), "solve_timing_begin")
+
+
+def solve_timing_end():
+    """-> {k: (calls, total ms)} for every solve launch since solve_timing_begin (CUDA events, native side)."""
+    calls = (ctypes.c_int64 * 33)()
+    ms = (ctypes.c_double * 33)()
+    check(_lib.load().eigd_solve_timing_end(ctypes.cast(calls, ctypes.c_void_p), ctypes.cast(ms, ctypes.c_void_p)),
+          "solve_timing_end")
+    return {k: (int(calls[k]), float(ms[k])) for k in range(33) if calls[k]}
+
+
 def launch_count():
     return int(_lib.load().eigd_launch_count())
 
@@ -461,6 +474,31 @@ class Factor:
         if tok:
             Timeline.end(tok, self.solve_bytes(B2.shape[1]), launch_count() - l0)
         return out
+
+
+def lanczos_extend(op, Bip, Vt, BVt, j0, j1, w, h, g, ab):
+    """Steps j0 .. j1-1 of the shift-and-invert Lanczos recurrence on the device (csrc/krylov.cu).
+
+    op: SpLuOperator (factor + shifted matrix for refinement); Bip: CsrDevice of the inner product;
+    Vt, BVt: (ncv + 1, n) row-major bases; w: (n,); h, g: (ncv + 1,); ab: (2, ncv + 1) [alpha; beta^2]."""
+    n = Vt.shape[1]
+    for t in (Vt, BVt, w, h, g, ab):
+        _chk(t)
+    if not (Vt.is_contiguous() and BVt.is_contiguous() and ab.is_contiguous() and w.is_contiguous()):
+        raise ValueError("lanczos_extend needs contiguous row-major bases")
+    refine = int(getattr(op, "refine", 0))
+    work2 = empty(2 * n) if refine else None
+    mat = op.mat
+    tok = Timeline.begin("lanczos")
+    l0 = launch_count() if tok else 0
+    check(_lib.load().eigd_lanczos_extend(op.lu.handle, refine, n, _ptr(mat.indptr), _ptr(mat.indices), _ptr(mat.data),
+                                          _ptr(Bip.indptr), _ptr(Bip.indices), _ptr(Bip.data), _ptr(Vt), _ptr(BVt),
+                                          Vt.stride(0), int(j0), int(j1), _ptr(w), _ptr(h), _ptr(g), _ptr(ab),
+                                          ab.stride(0), _ptr(_State.work), _ptr(work2)), "lanczos_extend")
+    nsteps = int(j1) - int(j0)
+    op.count += nsteps                      # one operator application per step, as SpLuOperator counts them
+    if tok:
+        Timeline.end(tok, 0, launch_count() - l0)
 
 
 # ------------------------------------------------------------------------------------------

@@ -573,6 +573,19 @@ def _replay(callback, hist):
                 callback(float(r))
 
 
+_PINNED = {}
+
+
+def _pinned(shape):
+    """Cached page-locked host buffer (cudaHostAlloc is too slow to repeat per call)."""
+    t = _PINNED.get(shape)
+    if t is None:
+        if len(_PINNED) > 16:
+            _PINNED.clear()
+        t = _PINNED[shape] = torch.empty(shape, dtype=torch.float64, pin_memory=True)
+    return t
+
+
 def _masked_inverse(vals, active):
     out = np.zeros_like(vals)
     ok = active & (vals > 0.0)
@@ -608,18 +621,17 @@ def _sibk_dev(Phib_d, Ad, Bd, lam, Phi_d, mode, psi_d, sigma, factor, rtol, atol
     Ycoef = np.zeros((maxiter, N))
     hdev = D.zeros(maxiter + 2, N)
     done = ~active
-    for j in range(1, maxiter + 1):
-        Z.append(factor.solve_dev(W[j - 1]))                                      # :1248
-        w = opmat.spmm(Z[j - 1])                                                  # :1250-1252
-        _project(BPhi, Phi_d, w)
-        for k in range(j - 1, -1, -1):                                            # modified Gram-Schmidt, descending (:1254-1257)
-            D.col_dot(w, W[k], out=hdev[k])
-            D.col_axpy(w, hdev[k], W[k], sign=-1.0)
-        _project(BPhi, Phi_d, w)                                                  # :1258
-        D.col_dot(w, w, out=hdev[j])
-        D.col_scale(w, hdev[j], mode=3)                                           # :1259-1260
-        W.append(w)
-        hcol = to_host(hdev[: j + 1])                                             # the one D2H of the iteration
+    # The Hessenberg column of iteration j is copied to pinned host memory asynchronously and the small
+    # least-squares problems (:1043-1049) are solved on the host WHILE the device already runs iteration
+    # j + 1 (its work does not depend on them; only the decision to stop does).  The price is one
+    # speculative iteration at the end, the gain is that the device never waits for the host.
+    hpin = _pinned((2, maxiter + 2, N))
+    events = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def host_step(j):
+        events[j & 1].synchronize()
+        XFER["d2h"] += (j + 1) * N * 8
+        hcol = hpin[j & 1, : j + 1].numpy().copy()
         hcol[j] = np.sqrt(hcol[j])
         H[:, : j + 1, j - 1] = hcol.T
         for i in np.nonzero(~done)[0]:
@@ -634,8 +646,30 @@ def _sibk_dev(Phib_d, Ad, Bd, lam, Phi_d, mode, psi_d, sigma, factor, rtol, atol
                 Ycoef[:j, i] = y
                 info[i] = j if ok else -1
                 done[i] = True
-        if done.all():
-            break
+
+    for j in range(1, maxiter + 1):
+        Z.append(factor.solve_dev(W[j - 1]))                                      # :1248
+        w = opmat.spmm(Z[j - 1])                                                  # :1250-1252
+        _project(BPhi, Phi_d, w)
+        for k in range(j - 1, -1, -1):                                            # modified Gram-Schmidt, descending (:1254-1257)
+            D.col_dot(w, W[k], out=hdev[k])
+            D.col_axpy(w, hdev[k], W[k], sign=-1.0)
+        _project(BPhi, Phi_d, w)                                                  # :1258
+        D.col_dot(w, w, out=hdev[j])
+        D.col_scale(w, hdev[j], mode=3)                                           # :1259-1260
+        W.append(w)
+        hpin[j & 1, : j + 1].copy_(hdev[: j + 1], non_blocking=True)
+        events[j & 1].record()
+        if j > 1:
+            host_step(j - 1)
+            if done.all():
+                factor.count -= N             # the speculative solve of iteration j is not part of the result
+                Z.pop()
+                break
+    else:
+        j = maxiter + 1
+    if not done.all():
+        host_step(j - 1 if j > maxiter else j)
     for jj, Zj in enumerate(Z):                                                   # psi_i += Z y  (:1275-1277)
         if np.any(Ycoef[jj]):
             D.col_axpy(psi_d, small_to_dev(Ycoef[jj]), Zj, sign=1.0)

@@ -118,11 +118,31 @@ int eigd_factor_info(eigd_factor* f, int64_t* info3);
 /* X = (L D L^T)^{-1} B in the original ordering; k columns, (rs, cs) strides; X may alias B */
 int eigd_factor_solve(eigd_factor* f, const double* d_B, int64_t brs, int64_t bcs,
                       double* d_X, int64_t xrs, int64_t xcs, int k);
+/* live timing of every solve launch between begin and end (CUDA events on the launching stream, used by
+ * bench.py for the roofline of the dominant kernel): calls_by_k / ms_by_k have 33 entries, index = number
+ * of right-hand sides of the launch */
+int eigd_solve_timing_begin(void);
+int eigd_solve_timing_end(int64_t* calls_by_k, double* ms_by_k);
 /* developer profiling of the persistent solve kernel: d_buf (device, (nphases + 1) x uint64) receives the
  * %globaltimer of CTA 0 at kernel start and after every phase of the following solves; NULL switches it off */
 int eigd_solve_set_phase_times(void* d_buf);
 int eigd_solve_num_phases(const eigd_factor* f);
 int64_t eigd_factor_bytes(const eigd_factor* f);
+
+/* ---- device-resident Lanczos recurrence: replaces the reverse-communication loop around ARPACK dsaupd
+ *      (eigd/arpack.py:438-442) and the step body of BasicLanczos.solve
+ *      (eigd/eigenvector_derivatives.py:1496-1545).  Runs steps j0 .. j1-1 without returning to the host:
+ *      w = factor^{-1} BV[j] (refine steps of iterative refinement against the shifted matrix `mat`, which
+ *      may be NULL when refine == 0), two classical Gram-Schmidt passes against V[0..j] in the B inner
+ *      product, BV[j+1] = B w, beta_j^2 = w . B w, V[j+1] = w / beta_j, BV[j+1] /= beta_j.
+ *      V, BV: (ncv + 1) x n row-major with leading dimension ld; w, h, g: n, ncv + 1, ncv + 1 doubles;
+ *      ab: 2 x ldab, row 0 <- alpha_j, row 1 <- beta_j^2; work >= eigd_gemm_tn_workspace() doubles;
+ *      work2: 2n doubles (refinement only). ------------------------------------------------------------ */
+int eigd_lanczos_extend(eigd_factor* f, int refine, int n, const int* d_mat_indptr, const int* d_mat_indices,
+                        const double* d_mat_vals, const int* d_b_indptr, const int* d_b_indices,
+                        const double* d_b_vals, double* d_V, double* d_BV, int64_t ld, int j0, int j1,
+                        double* d_w, double* d_h, double* d_g, double* d_ab, int ldab, double* d_work,
+                        double* d_work2);
 
 /* ---- element kernels: replaces the numpy einsum callbacks and assembly in
  *      examples/thermal.py:126-246, examples/natural_frequency.py:134-284 ------------------ */
