@@ -526,3 +526,53 @@ def q4_assemble(kind, conn, xy, ks, ms, cmat6, src_ptr, src, nnz, Kvals, Mvals):
 def node_gather(nptr, nelem, evals, scale, out):
     check(_lib.load().eigd_node_gather(out.numel(), _ptr(nptr), _ptr(nelem), _ptr(evals), float(scale), _ptr(out)), "node_gather")
     return out
+
+
+# ------------------------------------------------------------------------------------------
+# linearised buckling (csrc/buckling.cu)
+# ------------------------------------------------------------------------------------------
+def q4_stress(conn, xy, cmat6, ks, u, sdet):
+    check(_lib.load().eigd_q4_stress(conn.shape[0], _ptr(conn), _ptr(xy), _ptr(cmat6), _ptr(ks), _ptr(u), _ptr(sdet)),
+          "q4_stress")
+    return sdet
+
+
+def q4_assemble_geometric(conn, xy, sdet, src_ptr, src, nnz, Gvals):
+    check(_lib.load().eigd_q4_assemble_geometric(conn.shape[0], _ptr(conn), _ptr(xy), _ptr(sdet), _ptr(src_ptr), _ptr(src),
+                                                 int(nnz), _ptr(Gvals)), "q4_assemble_geometric")
+    return Gvals
+
+
+def q4_gderiv(conn, xy, cmat6, W, V, ks, dks, u, sx, out_rho=None, due=None):
+    """Fused sensitivities of sum_k w_k^T G(u, x) v_k (W, V: full-dof (2 nnodes, N) row-major)."""
+    if W.stride(1) != 1 or V.stride(1) != 1 or W.stride(0) != V.stride(0):
+        raise ValueError("W and V must share one row-major layout")
+    check(_lib.load().eigd_q4_gderiv(conn.shape[0], _ptr(conn), _ptr(xy), _ptr(cmat6), _ptr(W), _ptr(V), V.shape[1],
+                                     V.stride(0), _ptr(ks), _ptr(dks), _ptr(u), float(sx), _ptr(out_rho), _ptr(due)),
+          "q4_gderiv")
+
+
+def q4_dof_gather(nptr, nelem, nlocal, due, out):
+    check(_lib.load().eigd_q4_dof_gather(out.numel() // 2, _ptr(nptr), _ptr(nelem), _ptr(nlocal), _ptr(due), _ptr(out)),
+          "q4_dof_gather")
+    return out
+
+
+def expand_rows(idx, red, nfull):
+    """full[idx[i], :] = red[i, :], zeros elsewhere (examples/buckling.py full_vector)."""
+    r2 = _as2d(red)
+    k = r2.shape[1]
+    r2 = r2 if r2.is_contiguous() else r2.contiguous()
+    full = zeros(nfull, k)
+    check(_lib.load().eigd_expand_rows(idx.numel(), k, _ptr(idx), _ptr(r2), _ptr(full)), "expand_rows")
+    return full if red.dim() == 2 else full.reshape(-1)
+
+
+def reduce_rows(idx, full):
+    """red[i, :] = full[idx[i], :] (examples/buckling.py reduce_vector)."""
+    f2 = _as2d(full)
+    k = f2.shape[1]
+    f2 = f2 if f2.is_contiguous() else f2.contiguous()
+    red = empty(idx.numel(), k)
+    check(_lib.load().eigd_reduce_rows(idx.numel(), k, _ptr(idx), _ptr(f2), _ptr(red)), "reduce_rows")
+    return red if full.dim() == 2 else red.reshape(-1)

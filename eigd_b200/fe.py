@@ -219,10 +219,181 @@ class Q4Problem:
         return like_input(out, evals)
 
 
+def reduced_structure(indptr, indices, src_ptr, src, reduced, ndof):
+    """Pattern and (e, a, b) source lists of ``matrix[reduced, :][:, reduced]`` (examples/buckling.py:505-510)
+    taken from those of the full matrix; the result equals scipy's fancy-indexed CSR bit for bit
+    (``reduced`` ascending keeps rows and sorted columns in order)."""
+    reduced = np.asarray(reduced, dtype=np.int64)
+    f2r = np.full(ndof, -1, dtype=np.int64)
+    f2r[reduced] = np.arange(len(reduced))
+    rows = np.repeat(np.arange(ndof, dtype=np.int64), np.diff(indptr))
+    keep = (f2r[rows] >= 0) & (f2r[indices] >= 0)
+    cnt = np.zeros(len(reduced) + 1, dtype=np.int64)
+    np.add.at(cnt, f2r[rows[keep]] + 1, 1)
+    r_indptr = np.cumsum(cnt).astype(np.int32)
+    r_indices = f2r[indices[keep]].astype(np.int32)
+    lens = np.diff(src_ptr)[keep]
+    r_src_ptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    start = src_ptr[:-1][keep]
+    pos = np.repeat(start - r_src_ptr[:-1], lens) + np.arange(int(r_src_ptr[-1]), dtype=np.int64)
+    return r_indptr, r_indices, r_src_ptr, src[pos]
+
+
+class _BucklingCallback:
+    """dAdu / dAdx / dBdx of examples/buckling.py:924-979 as device operators on REDUCED (n_r, N) operands."""
+
+    def __init__(self, parent, which):
+        self.parent, self.which = parent, which
+        self.fused_with = None
+
+    def device_call(self, Wr, Vr):
+        pr = self.parent
+        W, V = pr.full_vector(Wr), pr.full_vector(Vr)
+        W2 = W if W.dim() == 2 else W.unsqueeze(1)
+        V2 = V if V.dim() == 2 else V.unsqueeze(1)
+        if self.which == "dGdu":
+            due = D.empty(pr.nelems, 8)
+            D.q4_gderiv(pr.conn_d, pr.xy_d, pr.cmat6_d, W2, V2, pr.kg_d, pr.dkg_d, pr.u_d, 1.0, None, due)
+            return D.q4_dof_gather(pr.nptr_d, pr.nelem_d, pr.nlocal_d, due, D.empty(pr.ndof))
+        out = D.zeros(pr.nelems)
+        if self.which == "dGdx":
+            D.q4_gderiv(pr.conn_d, pr.xy_d, pr.cmat6_d, W2, V2, pr.kg_d, pr.dkg_d, pr.u_d, 1.0, out, None)
+        else:                                                                     # dKdx
+            D.q4_quadforms(1, pr.conn_d, pr.xy_d, pr.cmat6_d, W2, None, V2, pr.base.dk_d, pr.base.dm_d, 1.0, 0.0, out)
+        return out
+
+    def __call__(self, w, v):
+        return like_input(self.device_call(to_dev(w), to_dev(v)), w)
+
+
+class BucklingQ4Problem:
+    """Plane-stress Q4 column of examples/buckling.py in HBM: K(x) with Dirichlet rows removed, the fundamental
+    path K_r u_r = f_r, the stress stiffness G(u, x) and the three sensitivity callbacks.
+
+    Element-level outputs stay per element (the node scatter ``np.add.at ... *0.25`` of :212-216, :337-341 is
+    linear and is applied once at the end by the driver).  Reference: examples/buckling.py:152-343, 499-518.
+    """
+
+    def __init__(self, conn, X, bcs, forces, E=1.0, nu=0.3, density=1.0, p=3.0, q=5.0, rho0_K=1e-6, rho0_G=1e-9,
+                 ptype_K="simp", ptype_G="simp"):
+        dev = D.dev()
+        self.base = Q4Problem(conn, X, "plane_stress", E=E, nu=nu, density=density, p=p, rho0_K=rho0_K,
+                              ptype_K=ptype_K, q=q)
+        b = self.base
+        self.conn, self.X = b.conn, b.X
+        self.nelems, self.nnodes, self.ndof = b.nelems, b.nnodes, b.ndof
+        self.conn_d, self.xy_d, self.cmat6_d = b.conn_d, b.xy_d, b.cmat6_d
+        self.nptr_d, self.nelem_d = b.nptr_d, b.nelem_d
+        # Dirichlet conditions and loads (:120-150)
+        fixed = np.zeros(self.ndof, dtype=bool)
+        for node, uv in bcs.items():
+            for index in uv:
+                fixed[2 * int(node) + int(index)] = True
+        self.reduced = np.nonzero(~fixed)[0]
+        self.nred = len(self.reduced)
+        self.f = np.zeros(self.ndof)
+        for node, fv in forces.items():
+            self.f[2 * int(node)] += fv[0]
+            self.f[2 * int(node) + 1] += fv[1]
+        src_ptr, src = to_host_i64(b.src_ptr_d), to_host_i64(b.src_d)
+        self.indptr, self.indices, r_src_ptr, r_src = reduced_structure(b.indptr, b.indices, src_ptr, src, self.reduced,
+                                                                        self.ndof)
+        self.nnz = len(self.indices)
+        self.indptr_d = torch.as_tensor(self.indptr, device=dev)
+        self.indices_d = torch.as_tensor(self.indices, device=dev)
+        self.src_ptr_d = torch.as_tensor(r_src_ptr, device=dev)
+        self.src_d = torch.as_tensor(r_src, device=dev)
+        self.reduced_d = torch.as_tensor(self.reduced.astype(np.int32), device=dev)
+        self.fr_d = to_dev(self.f[self.reduced])
+        # local index of every node inside each adjacent element (dof gather of :318-320)
+        e = np.repeat(np.arange(self.nelems, dtype=np.int64), 4)
+        v = self.conn.ravel()
+        loc = np.tile(np.arange(4, dtype=np.int64), self.nelems)
+        order = np.lexsort((e, v))
+        self.nlocal_d = torch.as_tensor(loc[order].astype(np.int32), device=dev)
+        # G material law (:231-234) and the derivative the reference applies to it (:333-336)
+        if ptype_G == "simp":
+            self.lawG, parG, pardG = 1, [p, 1.0, density, rho0_G], [p, 1.0, density, rho0_G]
+        elif ptype_G == "ramp":
+            self.lawG, parG, pardG = 2, [q, 1.0, density, rho0_G], [q + 1.0, 1.0, density, rho0_G]
+        else:
+            raise ValueError("unknown ptype_G %r" % ptype_G)
+        self._parG = (ctypes.c_double * 4)(*[float(t) for t in parG])
+        self._pardG = (ctypes.c_double * 4)(*[float(t) for t in pardG])
+        self.kg_d, self.dkg_d = D.empty(self.nelems), D.empty(self.nelems)
+        self._scratch = D.empty(self.nelems)
+        self.u_d = None
+        self.dGdu = _BucklingCallback(self, "dGdu")
+        self.dGdx = _BucklingCallback(self, "dGdx")
+        self.dKdx = _BucklingCallback(self, "dKdx")
+
+    # ---- Dirichlet maps (:499-518) ----------------------------------------------------------------
+    def full_vector(self, vr):
+        return D.expand_rows(self.reduced_d, vr, self.ndof)
+
+    def reduce_vector(self, v):
+        return D.reduce_rows(self.reduced_d, v)
+
+    def dof_coords(self):
+        """Per-dof coordinates of the reduced system for geometric nested dissection."""
+        return self.X[self.reduced // 2], 1
+
+    # ---- material ------------------------------------------------------------------------------------
+    def set_density(self, rho=None, rhoE=None):
+        rhoE_d = self.base.set_density(rho=rho, rhoE=rhoE)
+        lib = _lib.load()
+        s = self._scratch
+        _lib.check(lib.eigd_q4_material(self.lawG, self.nelems, None, _ptr(rhoE_d), self._parG, None, _ptr(self.kg_d),
+                                        _ptr(s), _ptr(self.dkg_d), _ptr(s)), "q4_material")
+        if self.lawG == 2:      # the reference differentiates the RAMP law of G with q + 1 (:336)
+            tmp = D.empty(self.nelems)
+            _lib.check(lib.eigd_q4_material(self.lawG, self.nelems, None, _ptr(rhoE_d), self._pardG, None, _ptr(tmp),
+                                            _ptr(s), _ptr(self.dkg_d), _ptr(s)), "q4_material")
+        return rhoE_d
+
+    # ---- assembly -------------------------------------------------------------------------------------
+    def assemble_K(self):
+        """K_r(rho) = reduce_matrix(get_stiffness_matrix(rhoE)) (:152-176, 505-510), values gathered directly
+        through the reduced source lists."""
+        b = self.base
+        Kv, Mv = D.empty(self.nnz), D.empty(self.nnz)
+        D.q4_assemble(1, self.conn_d, self.xy_d, b.ks_d, b.ms_d, self.cmat6_d, self.src_ptr_d, self.src_d, self.nnz, Kv, Mv)
+        return D.CsrDevice(self.indptr_d, self.indices_d, Kv, (self.nred, self.nred))
+
+    def set_displacement(self, ur_d):
+        """u = full_vector(u_r): the fundamental path the stress stiffness is linearised about (:561-562)."""
+        self.u_d = self.full_vector(ur_d)
+        return self.u_d
+
+    def assemble_G(self):
+        """G_r(u, rho) = reduce_matrix(get_stress_stiffness_matrix(rhoE, u)) (:220-255)."""
+        sdet = D.empty(self.nelems, 4, 3)
+        D.q4_stress(self.conn_d, self.xy_d, self.cmat6_d, self.kg_d, self.u_d, sdet)
+        Gv = D.empty(self.nnz)
+        D.q4_assemble_geometric(self.conn_d, self.xy_d, sdet, self.src_ptr_d, self.src_d, self.nnz, Gv)
+        return D.CsrDevice(self.indptr_d, self.indices_d, Gv, (self.nred, self.nred))
+
+    def dK_single(self, psi_full, u_full):
+        """psi^T (dK/drho_e) u per element for one pair of full vectors (:178-218 before the node scatter)."""
+        out = D.zeros(self.nelems)
+        b = self.base
+        D.q4_quadforms(1, self.conn_d, self.xy_d, self.cmat6_d, psi_full.reshape(-1, 1), None, u_full.reshape(-1, 1),
+                       b.dk_d, b.dm_d, 1.0, 0.0, out)
+        return out
+
+    def scatter_to_nodes(self, evals, scale=0.25):
+        return self.base.scatter_to_nodes(evals, scale)
+
+
+def to_host_i64(t):
+    return t.detach().cpu().numpy().astype(np.int64)
+
+
 class NodeFilter:
     """Conic node filter F[i, j] ~ max(0, r0 - |X_i - X_j|), rows normalised to 1
     (examples/node_filter.py:61-88), applied on the device as CSR products (:164-217).
-    Spatial filter without design-variable map or projection (the form the C1/C2/C5 models use)."""
+    Spatial filter with optional design-variable map (the symmetric column of examples/buckling.py:1331-1344),
+    without the tanh projection."""
 
     ftype = "spatial"
 
@@ -231,18 +402,33 @@ class NodeFilter:
         from scipy import sparse, spatial
         if ftype != "spatial":
             raise NotImplementedError("only the spatial (conic) filter is implemented")
-        if dvmap is not None or projection:
-            raise NotImplementedError("dvmap / projection are not implemented on the device filter")
+        if projection:
+            raise NotImplementedError("the tanh projection is not implemented on the device filter")
         self.X = np.asarray(X, dtype=np.float64)
         self.nnodes = self.X.shape[0]
         self.r0 = r0
-        self.num_design_vars = self.nnodes
         tree = spatial.cKDTree(self.X)
         Dm = tree.sparse_distance_matrix(tree, r0, output_type="coo_matrix")
         w = r0 - Dm.data
         F = sparse.coo_matrix((w, (Dm.row, Dm.col)), shape=(self.nnodes, self.nnodes)).tocsr()
         rs = np.asarray(F.sum(axis=1)).ravel()
         F = (sparse.diags(1.0 / rs) @ F).tocsr()
+        self.dvmap = None if dvmap is None else np.asarray(dvmap, dtype=np.int64)
+        self.offset_d = None
+        if self.dvmap is None:
+            self.num_design_vars = self.nnodes
+        else:
+            # design-variable map (examples/node_filter.py:164-168, 211-214): rho = F x[dvmap] with x := 1 where
+            # dvmap < 0, gradient scattered back with np.add.at.  Folded into the operator: F <- F P,
+            # P[i, dvmap[i]] = 1, plus the constant F 1_{dvmap<0}; the transpose product is then the gather form
+            # of the np.add.at scatter.
+            self.num_design_vars = int(num_design_vars if num_design_vars is not None else self.dvmap.max() + 1)
+            act = self.dvmap >= 0
+            P = sparse.coo_matrix((np.ones(int(act.sum())), (np.nonzero(act)[0], self.dvmap[act])),
+                                  shape=(self.nnodes, self.num_design_vars)).tocsr()
+            if not act.all():
+                self.offset_d = to_dev(F @ (~act).astype(np.float64))
+            F = (F @ P).tocsr()
         F.sort_indices()
         FT = F.T.tocsr()
         FT.sort_indices()
@@ -251,7 +437,10 @@ class NodeFilter:
         self.FT_d = D.CsrDevice.from_scipy(FT)
 
     def apply(self, x):
-        return like_input(self.F_d.spmm(to_dev(x)), x)
+        rho = self.F_d.spmm(to_dev(x))
+        if self.offset_d is not None:
+            D.axpby(1.0, rho, 1.0, self.offset_d, out=rho)
+        return like_input(rho, x)
 
     def apply_gradient(self, g, x=None, rho=None):
         return like_input(self.FT_d.spmm(to_dev(g)), g)

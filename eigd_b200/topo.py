@@ -209,3 +209,212 @@ def make_natural_frequency_model(nx=128, ny=64, Lx=2.0, Ly=1.0, rfact=4.0, **kwa
     conn, X = fe.grid_mesh(nx, ny, Lx, Ly)
     fltr = fe.NodeFilter(conn, X, r0=rfact * (Ly / ny))
     return NaturalFrequencyAnalysis(fltr, conn, X, **kwargs)
+
+
+# ------------------------------------------------------------------------------------------
+# linearised buckling -- examples/buckling.py
+# ------------------------------------------------------------------------------------------
+class BucklingTopologyAnalysis:
+    """examples/buckling.py ``TopologyAnalysis`` (:19-118): (K + BLF * G(u)) phi = 0 on the reduced dofs, with
+    the fundamental path K_r u_r = f_r, shift-invert about ``sigma`` (mode="buckling": A = G_r, B = K_r,
+    factor of K_r + sigma G_r, :548-640), and the gradient of an eigenvector functional including the
+    fundamental-path adjoint (:896-982).  Every vector of length n, 2*nnodes or nelems stays in HBM."""
+
+    def __init__(self, fltr, conn, X, bcs, forces={}, E=1.0, nu=0.3, ptype_K="simp", ptype_M="simp", ptype_G="simp",
+                 rho0_K=1e-6, rho0_M=1e-9, rho0_G=1e-9, p=3.0, q=5.0, density=1.0, sigma=3.0, N=10, m=None,
+                 solver_type="IRAM", tol=0.0, rtol=1e-10, eig_atol=1e-5, adjoint_method="shift-invert",
+                 adjoint_options=None, cost=1, deriv_type="tensor"):
+        self.fltr = fltr
+        self.conn, self.X = np.asarray(conn), np.asarray(X)
+        self.prob = fe.BucklingQ4Problem(self.conn, self.X, bcs, forces, E=E, nu=nu, density=density, p=float(p),
+                                         q=float(q), rho0_K=rho0_K, rho0_G=rho0_G, ptype_K=ptype_K.lower(),
+                                         ptype_G=ptype_G.lower())
+        self.nelems, self.nnodes, self.nvars = self.prob.nelems, self.prob.nnodes, self.prob.ndof
+        self.reduced, self.f = self.prob.reduced, self.prob.f
+        self.E, self.nu, self.p, self.q, self.density = E, nu, p, q, density
+        self.rho0_K, self.rho0_G = rho0_K, rho0_G
+        self.sigma, self.N, self.m = sigma, N, m
+        self.solver_type, self.tol, self.rtol, self.eig_atol = solver_type, tol, rtol, eig_atol
+        if adjoint_method == "shift-invert":
+            adjoint_method = "sibk"
+        self.adjoint_method = adjoint_method
+        self.adjoint_options = dict(adjoint_options or {})
+        self.cost, self.deriv_type = cost, deriv_type
+        self.x = 0.5 * np.ones(self.fltr.num_design_vars)                 # buckling.py:81
+        self.symbolic = None
+        self.sharding = None
+        self.Q = self.lam = None
+        self.profile = {"nnodes": self.nnodes, "nelems": self.nelems, "solver_type": solver_type,
+                        "adjoint_method": adjoint_method, "N": N}
+
+    # ---- forward (:548-640, 811-838) ----------------------------------------------------------------
+    def solve_eigenvalue_problem(self, store=False):
+        t0 = _now()
+        Kr = self.prob.assemble_K()
+        if self.symbolic is None:                                         # once per sparsity pattern
+            ts = _now()
+            coords, dofpn = self.prob.dof_coords()
+            sym = D.Symbolic(self.prob.indptr, self.prob.indices, self.prob.nred, coords=coords, dof_per_node=dofpn)
+            self.symbolic = (sym, sym.assembly_map_device(Kr.indptr, Kr.indices))
+            self.profile["symbolic analysis time"] = _now() - ts
+            t0 += self.profile["symbolic analysis time"]
+        self.Kfact = SpLuOperator(Kr, symbolic=self.symbolic, max_rhs=1)  # fundamental path K_r u_r = f_r
+        ur = self.Kfact.solve_dev(self.prob.fr_d)
+        self.u_d = self.prob.set_displacement(ur)
+        Gr = self.prob.assemble_G()
+        t1 = _now()
+        self.profile["matrix assembly time"] = t1 - t0
+        vals = D.axpby(1.0, Kr.data, float(self.sigma), Gr.data)          # K_r + sigma G_r on the shared pattern
+        self.factor = SpLuOperator(Kr.with_values(vals), symbolic=self.symbolic)
+        self.factor.count = 0
+        self.Kr, self.Gr = Kr, Gr
+        if self.solver_type == "IRAM":
+            if self.m is None:
+                self.m = max(2 * self.N + 1, 60)
+            self.eig_solver = IRAM(N=self.N, m=self.m, eig_atol=self.eig_atol, mode="buckling")
+        else:
+            if self.m is None:
+                self.m = max(3 * self.N + 1, 60)
+            self.eig_solver = BasicLanczos(N=self.N, m=self.m, eig_atol=self.eig_atol, tol=self.tol, mode="buckling")
+        self.eig_solver.sharding = self.sharding
+        mu, _ = self.eig_solver.solve(Gr, Kr, self.factor, self.sigma)
+        t2 = _now()
+        self.profile["solve preconditioner count"] = self.factor.count
+        self.profile["eigenvalue solve time"] = t2 - t1
+        self.profile["m"] = self.m
+        self.profile["eig_solver.m"] = str(self.eig_solver.m)
+        self.BLF = np.asarray(mu)[: self.N]
+        self.Qr = self.eig_solver._Phi_d                                   # (n_r, N) device
+        return self.BLF, self.Qr
+
+    def initialize(self, store=False, x=None):
+        if x is not None:
+            self.x = x
+        self.x_d = to_dev(self.x)
+        self.rho = self.fltr.apply(self.x_d)
+        self.rhoE = self.prob.set_density(rho=self.rho)
+        self.lam, self.Qr = self.solve_eigenvalue_problem(store)
+        return
+
+    @property
+    def u(self):
+        return to_host(self.u_d)
+
+    def compliance(self):
+        return float(np.dot(self.f, self.u))
+
+    def initialize_adjoint(self):
+        self.xb = D.zeros(self.x_d.shape[0])
+        self.rhoEb = D.zeros(self.nelems)
+        self.lamb = np.zeros(self.N)
+        self.Qrb = D.zeros(self.prob.nred, self.N)
+
+    # ---- objectives (:702-760) ----------------------------------------------------------------------
+    def _aggregate_weights(self, rho, mode):
+        lam = np.asarray(self.lam)
+        if mode == "exp":
+            eta = np.exp(-rho * (lam - np.min(lam)))
+            a = b = None
+        else:
+            a = np.tanh(rho * (lam - 0.0))
+            b = np.tanh(rho * (lam - 50.0))
+            eta = a - b
+        return eta / np.sum(eta), a, b
+
+    def get_eigenvector_aggregate(self, rho, node, mode="tanh"):
+        """h = sum_i eta_i Q[node, i]^2 (:702-724); as in the reference ``node`` indexes the FULL dof vector."""
+        eta, _, _ = self._aggregate_weights(rho, mode)
+        qn = self._dof_values(node)
+        return float(np.sum(eta * qn * qn))
+
+    def _dof_values(self, dof):
+        f2r = np.full(self.nvars, -1, dtype=np.int64)
+        f2r[self.reduced] = np.arange(len(self.reduced))
+        r = int(f2r[dof])
+        self._dof_row = r
+        return to_host(self.Qr[r]) if r >= 0 else np.zeros(self.N)
+
+    def add_eigenvector_aggregate_derivative(self, hb, rho, node, mode="tanh"):
+        """Seeds of h = sum_i eta_i Q[node, i]^2 (:726-760): Qrb[row(node), i] += 2 hb eta_i Q[node, i] and
+        lamb_i -= hb rho eta_i (a_i + b_i) (Q[node, i]^2 - h)."""
+        eta, a, b = self._aggregate_weights(rho, mode)
+        qn = self._dof_values(node)
+        h = float(np.sum(eta * qn * qn))
+        if self._dof_row >= 0:
+            row = self.Qrb[self._dof_row]
+            row += small_to_dev(2.0 * hb * eta * qn)
+        if mode == "exp":
+            self.lamb -= hb * rho * eta * (qn * qn - h)
+        else:
+            self.lamb -= hb * rho * eta * (a + b) * (qn * qn - h)
+        return h
+
+    # ---- reverse (:866-982) -------------------------------------------------------------------------
+    def finalize_adjoint(self):
+        res_list = []
+        self.factor.count = 0
+        t0 = _now()
+        psir, corr_data = self.eig_solver.solve_adjoint(self.Qrb, rtol=self.rtol, method=self.adjoint_method,
+                                                        callback=res_list.append, **self.adjoint_options)
+        t1 = _now()
+        self.psir = psir
+        self.profile["adjoint preconditioner count"] = self.factor.count
+        self.profile["adjoint solution time"] = t1 - t0
+        self.profile["adjoint residuals"] = res_list
+        self.profile["adjoint iterations"] = len(res_list)
+        self.profile["adjoint correction data"] = corr_data
+        pr = self.prob
+        # d/du of the eigen-terms: dfdu0 = sum_i w_i^T (dG/du) phi_i  (dB/du = 0: K does not depend on u)
+        dfdu0 = D.zeros(self.nvars)
+        self.eig_solver.add_total_derivative(self.lamb, self.Qrb, psir, pr.dGdu, None, dfdu0, adj_corr_data=corr_data,
+                                             deriv_type=self.deriv_type)
+        # explicit design dependence of G and K
+        self.eig_solver.add_total_derivative(self.lamb, self.Qrb, psir, pr.dGdx, pr.dKdx, self.rhoEb,
+                                             adj_corr_data=corr_data, deriv_type=self.deriv_type)
+        # adjoint of the fundamental path: K_r psi_u = -dfdu0_r, rhob += psi_u^T (dK/drho) u   (:974-979)
+        psiu_r = self.Kfact.solve_dev(pr.reduce_vector(dfdu0))
+        psiu = pr.full_vector(psiu_r)
+        D.axpby(1.0, self.rhoEb, -1.0, pr.dK_single(psiu, self.u_d), out=self.rhoEb)
+        self.rhob = pr.scatter_to_nodes(self.rhoEb)
+        g = self.fltr.apply_gradient(self.rhob, self.x_d)
+        D.axpby(1.0, self.xb, 1.0, g, out=self.xb)
+        t2 = _now()
+        self.profile["total derivative time"] = t2 - t1
+        return
+
+    def time_to_gradient(self):
+        p = self.profile
+        return p["eigenvalue solve time"] + p["adjoint solution time"] + p["total derivative time"]
+
+
+def domain_compressed_column(nx=64, ny=128, Lx=1.0, Ly=2.0, shear_force=False):
+    """examples/buckling.py ``domain_compressed_column`` (:1300-1369), vectorised: mesh, left-right symmetry map
+    of the design variables, clamped bottom edge, compressive (or shear) load on the top edge."""
+    conn, X = fe.grid_mesh(nx, ny, Lx, Ly)
+    nodes = np.arange((nx + 1) * (ny + 1), dtype=np.int64).reshape(nx + 1, ny + 1)
+    dvmap = np.zeros((nx + 1, ny + 1), dtype=np.int64)
+    index = 0
+    for i in range(nx // 2 + 1):                      # same visiting order as the reference (:1336-1341)
+        dvmap[i, :] = index + np.arange(ny + 1)
+        dvmap[nx - i, :] = dvmap[i, :]
+        index += ny + 1
+    bcs = {int(nodes[i, 0]): [0, 1] for i in range(nx + 1)}
+    P = 1e-3
+    forces = {}
+    if shear_force:
+        for i in range(nx + 1):
+            forces[int(nodes[i, ny])] = [P / (nx + 1), 0]
+    else:
+        offset = int(np.ceil(nx / 30))
+        for i in range(offset):
+            forces[int(nodes[nx // 2 - i - 1, ny])] = [0, -P / (2 * offset + 1)]
+            forces[int(nodes[nx // 2 + i + 1, ny])] = [0, -P / (2 * offset + 1)]
+        forces[int(nodes[nx // 2, ny])] = [0, -P / (2 * offset + 1)]
+    return conn, X, dvmap.flatten(), index, bcs, forces
+
+
+def make_buckling_model(nx=64, ny=128, Lx=1.0, Ly=2.0, rfact=4.0, N=10, shear_force=False, **kwargs):
+    """examples/buckling.py ``make_model`` (:1372-1409)."""
+    conn, X, dvmap, ndv, bcs, forces = domain_compressed_column(nx=nx, ny=ny, Lx=Lx, Ly=Ly, shear_force=shear_force)
+    fltr = fe.NodeFilter(conn, X, r0=rfact * (Lx / nx), dvmap=dvmap, num_design_vars=ndv)
+    return BucklingTopologyAnalysis(fltr, conn, X, bcs=bcs, forces=forces, N=N, **kwargs)

@@ -171,6 +171,28 @@ int eigd_q4_material(int law, int nelems, const int* d_conn, const double* d_rho
 /* node_out[v] = scale * sum_{e in adj(v)} e_vals[e]   (gather form of np.add.at, thermal.py:612-615) */
 int eigd_node_gather(int nnodes, const int* d_nptr, const int* d_nelem, const double* d_evals, double scale, double* d_out);
 
+/* ---- linearised buckling (examples/buckling.py): stress stiffness G(u, x) and its sensitivities ---------
+ * All vectors are in the FULL dof numbering (2 dof per node); eigd_expand_rows / eigd_reduce_rows are the
+ * Dirichlet maps full_vector / reduce_vector (examples/buckling.py:499-518). */
+/* sdet[e][q][i] = detJ_q ks[e] (C0 Be(q) u_e)_i, q = 4 Gauss points, i = 3 stress components (:241-247) */
+int eigd_q4_stress(int nelems, const int* d_conn, const double* d_xy, const double* d_cmat6, const double* d_ks,
+                   const double* d_u, double* d_sdet);
+/* gather-form assembly of G through the same (element, a, b) -> CSR source lists as K (:249-255) */
+int eigd_q4_assemble_geometric(int nelems, const int* d_conn, const double* d_xy, const double* d_sdet,
+                               const int64_t* d_src_ptr, const int64_t* d_src, int64_t nnz, double* d_Gvals);
+/* fused sensitivities of sum_k w_k^T G(u, x) v_k: out_rho[e] += sx * dks[e] * (...) (:324-343, per element, before
+ * the node scatter) and due[e][8] = ks[e] * (...) (:312-322, before the dof scatter); either output may be NULL.
+ * W, V: (2*nnodes, N) row-major with leading dimension ldw. */
+int eigd_q4_gderiv(int nelems, const int* d_conn, const double* d_xy, const double* d_cmat6, const double* d_W,
+                   const double* d_V, int N, int ldw, const double* d_ks, const double* d_dks, const double* d_u,
+                   double sx, double* d_out_rho, double* d_due);
+/* dfdu[2v + d] = sum_{e around v} due[e][2 local + d] (gather form of np.add.at, :318-320) */
+int eigd_q4_dof_gather(int nnodes, const int* d_nptr, const int* d_nelem, const int* d_nlocal, const double* d_due,
+                       double* d_out);
+/* full[idx[i], :] = red[i, :] and red[i, :] = full[idx[i], :], k columns, row-major */
+int eigd_expand_rows(int64_t nr, int k, const int* d_idx, const double* d_red, double* d_full);
+int eigd_reduce_rows(int64_t nr, int k, const int* d_idx, const double* d_full, double* d_red);
+
 #ifdef __cplusplus
 }
 #endif

@@ -108,7 +108,7 @@ def buckling_case(solver_type="BasicLanczos", methods=("sibk", "pcpg"), nx=16, n
     for method in methods:
         opts = dict(SIBK) if method == "sibk" else {"lanczos_guess": True}
         np.random.seed(seed)
-        topo = bk.make_model(nx=nx, ny=ny, N=N, m=24, sigma=3.0, solver_type=solver_type, adjoint_method=method,
+        topo = bk.make_model(nx=nx, ny=ny, N=N, m=60, sigma=3.0, solver_type=solver_type, adjoint_method=method,
                              adjoint_options=opts, rtol=1e-12, deriv_type="tensor")
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
@@ -123,10 +123,22 @@ def buckling_case(solver_type="BasicLanczos", methods=("sibk", "pcpg"), nx=16, n
             es = topo.eig_solver
             out.update(dict(sigma=topo.sigma, N=N, m=es.m, m_max=es.m_max, lam=topo.lam.copy(), Phi=topo.Qr.copy(), Phib=topo.Qrb.copy(),
                             lamb=topo.lamb.copy(), reduced=np.array(topo.reduced), u=topo.u.copy(), rhoE=topo.rhoE.copy(),
-                            conn=topo.conn, X=topo.X, node=node, nx=nx, ny=ny))
+                            conn=topo.conn, X=topo.X, node=node, nx=nx, ny=ny,
+                            f=topo.f.copy(), material=np.array([topo.E, topo.nu, topo.p, topo.rho0_K, topo.rho0_G]),
+                            BLF=np.asarray(topo.BLF).copy()))
+            # element callbacks of the example on seeded operands (isolates the sensitivity kernels from the solvers)
+            rng = np.random.default_rng(7)
+            Wr, Vr = rng.normal(size=topo.Qr.shape), rng.normal(size=topo.Qr.shape)
+            Wf, Vf = topo.full_vector(Wr), topo.full_vector(Vr)
+            dfds = topo.intital_stress_stiffness_matrix_deriv(topo.rhoE, topo.Te, topo.detJ, Wf, Vf)
+            out.update(dict(cb_W=Wr, cb_V=Vr,
+                            cb_dGdu=topo.get_stress_stiffness_matrix_uderiv_tensor(dfds, topo.Be),
+                            cb_dGdx=topo.get_stress_stiffness_matrix_xderiv_tensor(topo.rhoE, topo.u, dfds, topo.Be),
+                            cb_dKdx=topo.get_stiffness_matrix_deriv(topo.rhoE, Wf, Vf)))
         out["psi_" + method] = topo.psir.copy()
         out["corr_" + method] = corr_to_array(topo.profile["adjoint correction data"])
         out["xb_" + method] = topo.xb.copy()
+        out["rhob_" + method] = topo.rhob.copy()          # nodal gradient before the filter transpose
     return out
 
 
@@ -139,7 +151,10 @@ if __name__ == "__main__":
         "nf_iram": nf_case,
         "buckling_basiclanczos": buckling_case,
     }
+    only = set(sys.argv[1:])
     for name, fn in cases.items():
+        if only and name not in only:
+            continue
         d = fn()
         path = os.path.join(HERE, name + ".npz")
         np.savez_compressed(path, **d)
