@@ -641,7 +641,7 @@ static void factor_layout(const eigd_symbolic* s, const SymDevHolder* h, int max
   sz[5] = align256(h->panel_total * 8);                // sbwd
   sz[6] = align256((int64_t)s->n * 8);                 // dval
   sz[7] = align256((int64_t)s->n * 8);                 // dinv
-  sz[8] = align256((int64_t)(SOLVE_NSLAB + 1) * sumf * kc * 8);   // wbuf: direct child slabs + overflow slab, one plane per right-hand side
+  sz[8] = align256(3 * sumf * kc * 8);                 // wbuf: three child slabs, one plane per right-hand side
   sz[9] = align256((int64_t)s->n * kc * 8);            // ybuf
   sz[10] = align256((int64_t)s->n * kc * 8);           // xperm
   sz[11] = 256;                                        // amax

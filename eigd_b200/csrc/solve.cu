@@ -28,8 +28,6 @@
 namespace {
 
 constexpr int MAX_PHASES_SMEM = 96;
-constexpr int MAX_SUB_LEVELS = 32;
-constexpr int REC_CAP = 512;          // subtree tile records staged in shared memory per slot (48 B each)
 
 struct SolveArgs {
   const TileRec* tiles;
@@ -60,68 +58,38 @@ struct SolveArgs {
   unsigned long long* times;      // developer profiling: %globaltimer of CTA 0 after every phase (NULL: off)
 };
 
-// Vectors produced earlier in the same launch by other SMs are read through L2 (ld.global.cg): L1 is not
-// coherent across SMs and a line fetched in an earlier phase may be stale.
-//
-// Every operand loader below first ISSUES all its loads into registers and only then combines them: the
-// per-tile critical path is one memory round trip, not one per operand (measured: `v += ld(..)` chains cost
-// three to four exposed L2/DRAM latencies per tile, 1.5 - 4 us, which is what bounded the solve).
+// vectors produced earlier in the same launch by other SMs are read through L2 (ld.global.cg): L1 is
+// not coherent across SMs and a line fetched in an earlier phase may be stale
 template <int KT>
-struct RhsGroup {           // right-hand sides handled per batch of loads (register budget: 5 loads each)
-  static constexpr int value = KT % 4 == 0 ? 4 : (KT % 2 == 0 ? 2 : 1);
-};
+__device__ __forceinline__ void add_row(const double* __restrict__ base, int64_t row, int k, double* v) {
+  const double* p = base + row * k;
+#pragma unroll
+  for (int r = 0; r < KT; ++r)
+    if (r < k) v[r] += __ldcg(p + r);
+}
 
-// v[0:k) = (brow >= 0 ? bperm[brow, :] : 0) + the forward-sweep updates addressed to w-row t: the direct
-// child slabs the front's children actually write (fixed order), then the overflow list
+// v += the forward-sweep updates addressed to w-row t: slab 0 + slab 1 (+ overflow list), fixed order
 template <int KT>
-__device__ __forceinline__ void fwd_operand(const SolveArgs& a, int64_t t, int64_t brow, int64_t link, double* v) {
-  constexpr int G = RhsGroup<KT>::value;
-  const int k = a.k;
-  const int nsl = (int)((link >> LINK_NSLAB_SHIFT) & 7);
-  const double* w0 = a.wbuf + t;
-  const double* bp = a.bperm + (brow >= 0 ? brow : 0) * k;
+__device__ __forceinline__ void child_add(const SolveArgs& a, int64_t t, int64_t link, double* v) {
+  if (!(link & LINK_HAS_CHILDREN)) return;
+  const double* p0 = a.wbuf + t;
+  const double* p1 = p0 + a.slab_stride;
 #pragma unroll
-  for (int r0 = 0; r0 < KT; r0 += G) {
-    double b[G], s[SOLVE_NSLAB][G];
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-      const int r = r0 + g;
-      const bool ok = r < k;
-      b[g] = (ok && brow >= 0) ? __ldcg(bp + r) : 0.0;
-#pragma unroll
-      for (int sl = 0; sl < SOLVE_NSLAB; ++sl)
-        s[sl][g] = (ok && sl < nsl) ? __ldcg(w0 + sl * a.slab_stride + (int64_t)r * a.sumf) : 0.0;
-    }
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-      double acc = b[g];
-#pragma unroll
-      for (int sl = 0; sl < SOLVE_NSLAB; ++sl) acc += s[sl][g];
-      v[r0 + g] = acc;
-    }
-  }
+  for (int r = 0; r < KT; ++r)
+    if (r < a.k) v[r] += __ldcg(p0 + (int64_t)r * a.sumf) + __ldcg(p1 + (int64_t)r * a.sumf);
   if (link & LINK_HAS_OVF) {
     const int o = __ldg(&a.ovf_row[t]);
     if (o >= 0) {
       const int cnt = __ldg(&a.ovf[o]);
-      const double* p2 = a.wbuf + SOLVE_NSLAB * a.slab_stride;
-#pragma unroll 1
+      const double* p2 = a.wbuf + 2 * a.slab_stride;
       for (int q = 0; q < cnt; ++q) {
         const int64_t src = __ldg(&a.ovf[o + 1 + q]);
 #pragma unroll
         for (int r = 0; r < KT; ++r)
-          if (r < k) v[r] += __ldcg(p2 + (int64_t)r * a.sumf + src);
+          if (r < a.k) v[r] += __ldcg(p2 + (int64_t)r * a.sumf + src);
       }
     }
   }
-}
-
-// v[0:k) = base[row, :]
-template <int KT>
-__device__ __forceinline__ void load_row(const double* __restrict__ base, int64_t row, int k, double* v) {
-  const double* p = base + row * k;
-#pragma unroll
-  for (int r = 0; r < KT; ++r) v[r] = r < k ? __ldcg(p + r) : 0.0;
 }
 
 __device__ __forceinline__ TileRec unpack_tile(int4 a, int4 b, int4 c) {
@@ -141,83 +109,45 @@ __device__ __forceinline__ TileRec load_tile(const TileRec* p) {
 
 // acc += M[out, c0:c1) * in[c0:c1) for this lane's output; M column-major with leading dimension ld.
 // stage_fn(c, v) fills v[0:k) with input vector entry c (lane-parallel over the chunk of 32 columns),
-// the chunk is then shared through the warp's staging buffer ([32 columns][KT], so that one column's KT
-// values are one or a few 16-byte shared loads).
-// The loop is written for a SHORT instruction stream: ncu showed the previous fully unrolled, predicated
-// 32-slot body (~2500 SASS instructions per chunk, 64-bit multiplies for every address) made the solve
-// issue-bound -- 16 warps x 2500 instructions per round of tiles is 5 us on an SM.  Here a column costs one
-// pointer add, one predicated load and KT (LDS +) DFMA.  Memory-level parallelism still comes from the
-// instruction stream: MB independent 8-byte panel loads per lane (256 B per warp each) are in flight while
-// the previous batch is consumed, and the first batch is requested BEFORE the gather of the input vector.
+// the chunk is then shared through the warp's staging buffer.  Memory-level parallelism comes from the
+// instruction stream, not from occupancy: the panel entries of a sub-chunk are requested back to back
+// (MC independent 8-byte loads per lane, 256 B per warp each) BEFORE the gather of the input vector, so
+// one DRAM round trip covers MC columns.
 template <int KT, class StageFn>
 __device__ __forceinline__ void warp_panel_product(const double* __restrict__ M, int64_t ld, int c0, int c1, int lane,
                                                    double* stage, double* acc, StageFn stage_fn) {
-  constexpr int MB = KT <= 2 ? 16 : 8;
+  constexpr int MC = KT <= 2 ? 32 : (KT <= 10 ? 16 : 8);
+  constexpr int g = 0, nks = 1;
   for (int cc = c0; cc < c1; cc += 32) {
     const int ncol = min(32, c1 - cc);
-    const double* p = M + (int64_t)cc * ld;
-    double m[MB];
+    const double* Mc = M + (int64_t)(cc + g) * ld;
+    const int64_t step = (int64_t)nks * ld;
+    double m[MC];
 #pragma unroll
-    for (int j = 0; j < MB; ++j) {
-      m[j] = j < ncol ? __ldg(p) : 0.0;
-      p += ld;
-    }
+    for (int j = 0; j < MC; ++j) m[j] = (g + j * nks < ncol) ? __ldg(Mc + j * step) : 0.0;
     double v[KT];
 #pragma unroll
     for (int r = 0; r < KT; ++r) v[r] = 0.0;
     if (lane < ncol) stage_fn(cc + lane, v);
-    if constexpr (KT % 2 == 0) {
-      double2* s2 = reinterpret_cast<double2*>(stage + lane * KT);
 #pragma unroll
-      for (int r = 0; r < KT / 2; ++r) s2[r] = make_double2(v[2 * r], v[2 * r + 1]);
-    } else {
-#pragma unroll
-      for (int r = 0; r < KT; ++r) stage[lane * KT + r] = v[r];
-    }
+    for (int r = 0; r < KT; ++r) stage[r * 32 + lane] = v[r];
     __syncwarp();
-    for (int j0 = 0; j0 < ncol; j0 += MB) {
-      double mn[MB];
-      const int rem = ncol - j0 - MB;                      // columns left after this batch
-      if (rem > 0) {
 #pragma unroll
-        for (int j = 0; j < MB; ++j) {
-          mn[j] = j < rem ? __ldg(p) : 0.0;
-          p += ld;
-        }
-      }
-      const double* sj = stage + j0 * KT;
+    for (int j = 0; j < MC; ++j)
 #pragma unroll
-      for (int j = 0; j < MB; ++j) {
-        if constexpr (KT % 2 == 0) {
-          const double2* s2 = reinterpret_cast<const double2*>(sj + j * KT);
+      for (int r = 0; r < KT; ++r) acc[r] = fma(m[j], stage[r * 32 + ((g + j * nks) & 31)], acc[r]);
+    if (MC < 32) {
+      for (int j0 = MC; g + j0 * nks < ncol; j0 += MC) {          // warp-uniform trip count is not needed: no sync inside
 #pragma unroll
-          for (int r = 0; r < KT / 2; ++r) {
-            const double2 t = s2[r];
-            acc[2 * r] = fma(m[j], t.x, acc[2 * r]);
-            acc[2 * r + 1] = fma(m[j], t.y, acc[2 * r + 1]);
-          }
-        } else {
+        for (int j = 0; j < MC; ++j) m[j] = (g + (j0 + j) * nks < ncol) ? __ldg(Mc + (j0 + j) * step) : 0.0;
 #pragma unroll
-          for (int r = 0; r < KT; ++r) acc[r] = fma(m[j], sj[j * KT + r], acc[r]);
-        }
-      }
-      if (rem > 0) {
+        for (int j = 0; j < MC; ++j)
 #pragma unroll
-        for (int j = 0; j < MB; ++j) m[j] = mn[j];
+          for (int r = 0; r < KT; ++r) acc[r] = fma(m[j], stage[r * 32 + ((g + (j0 + j) * nks) & 31)], acc[r]);
       }
     }
     __syncwarp();
   }
-}
-
-// L2 prefetch of [p, p + bytes): a hint, so the 16-byte alignment the instruction asks for is met by widening
-// the range (panel storage is padded to 256 B, the widened range stays inside the allocation)
-__device__ __forceinline__ void prefetch_l2(const void* p, unsigned bytes) {
-  const unsigned long long addr = (unsigned long long)p;
-  const unsigned long long a0 = addr & ~15ull;
-  const unsigned long long a1 = (addr + bytes + 15ull) & ~15ull;
-  const unsigned sz = (unsigned)(a1 - a0);
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"(sz) : "memory");
 }
 
 __device__ __forceinline__ void grid_barrier(unsigned long long* ctr, unsigned long long target) {
@@ -232,98 +162,66 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* ctr, unsigned l
   __syncthreads();
 }
 
-// One warp tile: 32 consecutive outputs of one front, slice `slice` of `ws` of its reduction dimension.
-// Forward (dir 0): outputs are front rows, acc = S[row, 0:cend) w1 (+ the children's updates of the row);
-// backward (dir 1): outputs are pivot columns, acc = S^T[col, o0:f) [z1 ; x2].
-// Both directions go through ONE instance of warp_panel_product (the direction is a run-time branch in the
-// gather), and both kinds of phase through one call site: the kernel's code footprint and register
-// pressure, not DRAM, were what bounded the previous version.
-// aux: what the store of this lane's output needs (forward pivot row: D^-1 entry; forward update row: its
-// position in the parent front; backward: the original index of the column), requested here, at the top of
-// the tile, so that the store does not start with a dependent look-up.
-// panel slice of a tile: M = first output row (forward) / pivot column (backward) of the tile in the column-major
-// panel with leading dimension ld, [c0, c1) = the part of the reduction dimension slice `slice` of `ws` covers
-__device__ __forceinline__ void tile_range(const SolveArgs& a, int dir, const TileRec& tr, int slice, int ws,
-                                           const double*& M, int& ld, int& c0, int& c1) {
-  const int nc = tr.nc, f = tr.nc + tr.nb;
-  const int o0 = tr.tile * SOLVE_TILE;
-  if (dir == 0) {
-    const int cend = min(nc, o0 + SOLVE_TILE);          // S is lower triangular inside the pivot rows
-    const int per = (cend + ws - 1) / ws;
-    c0 = slice * per;
-    c1 = min(cend, c0 + per);
-    M = a.sfwd + tr.soff + o0;
-    ld = f;
-  } else {
-    const int len = f - o0;
-    const int per = (len + ws - 1) / ws;
-    c0 = o0 + slice * per;
-    c1 = min(f, c0 + per);
-    M = a.sbwd + tr.soff + o0;
-    ld = nc;
-  }
-}
-
-struct TileAux {
-  double d;
-  int i;
-};
-
+// the products of one warp tile: slice `slice` of `ws` of the reduction dimension.
+// use_perm: the right-hand side is gathered from B through perm (first phase; later phases read the
+// permuted copy written during the first one)
 template <int KT>
-__device__ __forceinline__ TileAux tile_compute(const SolveArgs& a, int dir, const TileRec& tr, int lane, int slice, int ws,
-                                                double* stage, double* acc) {
+__device__ __forceinline__ void tile_compute(const SolveArgs& a, int dir, bool use_perm, const TileRec& tr, int lane,
+                                             int slice, int ws, double* stage, double* acc) {
+  constexpr int to = SOLVE_TILE;
   const int k = a.k;
   const int nc = tr.nc, f = tr.nc + tr.nb;
-  const int o0 = tr.tile * SOLVE_TILE;
-  const int out = o0 + lane;
-  const double* M;
-  int ld, c0, c1;
-  TileAux aux;
-  aux.d = 0.0;
-  aux.i = 0;
-  const bool upd = dir == 0 && slice == 0 && out >= nc && out < f;      // forward update row owned by this lane
-  if (slice == 0) {
-    if (dir == 0) {
-      if (out < nc) aux.d = __ldg(&a.dinv[tr.first + out]);
-      else if (out < f) aux.i = __ldg(&a.rel[tr.row_off + out - nc]);
-    } else if (out < nc) {
-      aux.i = __ldg(&a.perm[tr.first + out]);
-    }
+  const int o0 = tr.tile * to;
+  const int out = o0 + (lane % to);
+  if (dir == 0) {
+    // ---- forward: outputs are front rows; acc = S[row, 0:cend) w1 (+ the children's updates of the row)
+    if (slice == 0 && lane < to && out >= nc && out < f) child_add<KT>(a, tr.w_off + out, tr.link, acc);
+    const int cend = min(nc, o0 + to);                  // S is lower triangular inside the pivot rows
+    const int per = (cend + ws - 1) / ws;
+    const int c0 = slice * per, c1 = min(cend, c0 + per);
+    const double* M = a.sfwd + tr.soff + min(out, f - 1);
+    warp_panel_product<KT>(M, f, c0, c1, lane, stage, acc, [&](int c, double* v) {
+      if (use_perm) {
+        const int64_t po = __ldg(&a.perm[tr.first + c]);
+        const double* bp = a.B + po * a.brs;
+#pragma unroll
+        for (int r = 0; r < KT; ++r)
+          if (r < k) v[r] = bp[(int64_t)r * a.bcs];
+      } else {
+        add_row<KT>(a.bperm, tr.first + c, k, v);
+      }
+      child_add<KT>(a, tr.w_off + c, tr.link, v);
+    });
+  } else {
+    // ---- backward: outputs are pivot columns; acc = S^T[col, o0:f) [z1 ; x2]
+    const int len = f - o0;
+    const int per = (len + ws - 1) / ws;
+    const int i0 = o0 + slice * per, i1 = min(f, i0 + per);
+    const double* M = a.sbwd + tr.soff + min(out, nc - 1);
+    warp_panel_product<KT>(M, nc, i0, i1, lane, stage, acc, [&](int i, double* v) {
+      if (i < nc) add_row<KT>(a.ybuf, tr.first + i, k, v);
+      else add_row<KT>(a.xperm, __ldg(&a.sn_rows[tr.row_off + i - nc]), k, v);
+    });
   }
-  double u[KT];
-#pragma unroll
-  for (int r = 0; r < KT; ++r) u[r] = 0.0;
-  if (KT <= 4 && upd && (tr.link & LINK_HAS_CHILDREN)) fwd_operand<KT>(a, tr.w_off + out, -1, tr.link, u);
-  tile_range(a, dir, tr, slice, ws, M, ld, c0, c1);
-  M += min(lane, (dir == 0 ? f : nc) - 1 - o0);
-  warp_panel_product<KT>(M, ld, c0, c1, lane, stage, acc, [&](int c, double* v) {
-    if (dir == 0) fwd_operand<KT>(a, tr.w_off + c, tr.first + c, tr.link, v);
-    else if (c < nc) load_row<KT>(a.ybuf, tr.first + c, k, v);
-    else load_row<KT>(a.xperm, __ldg(&a.sn_rows[tr.row_off + c - nc]), k, v);
-  });
-  if (KT > 4 && upd && (tr.link & LINK_HAS_CHILDREN)) fwd_operand<KT>(a, tr.w_off + out, -1, tr.link, u);
-#pragma unroll
-  for (int r = 0; r < KT; ++r) acc[r] += u[r];
-  return aux;
 }
 
 template <int KT>
-__device__ __forceinline__ void tile_store(const SolveArgs& a, int dir, const TileRec& tr, int lane, const TileAux& aux,
-                                           const double* acc) {
+__device__ __forceinline__ void tile_store(const SolveArgs& a, int dir, const TileRec& tr, int lane, const double* acc) {
   const int k = a.k;
   const int nc = tr.nc, f = tr.nc + tr.nb;
   const int out = tr.tile * SOLVE_TILE + lane;
   if (dir == 0) {
     if (out < nc) {
+      const double di = __ldg(&a.dinv[tr.first + out]);
       double* y = a.ybuf + (int64_t)(tr.first + out) * k;
 #pragma unroll
       for (int r = 0; r < KT; ++r)
-        if (r < k) y[r] = aux.d * acc[r];
+        if (r < k) y[r] = di * acc[r];
     } else if (out < f) {
       const int slab = (int)((tr.link >> LINK_SLAB_SHIFT) & 0xff);
       int64_t dst;                                            // row in the plane of the destination slab
-      if (slab < SOLVE_NSLAB) dst = slab * a.slab_stride + (tr.link & LINK_WOFF_MASK) + aux.i;
-      else dst = SOLVE_NSLAB * a.slab_stride + tr.w_off + out;
+      if (slab < 2) dst = slab * a.slab_stride + (tr.link & LINK_WOFF_MASK) + __ldg(&a.rel[tr.row_off + out - nc]);
+      else dst = 2 * a.slab_stride + tr.w_off + out;
       double* w = a.wbuf + dst;
 #pragma unroll
       for (int r = 0; r < KT; ++r)
@@ -331,7 +229,7 @@ __device__ __forceinline__ void tile_store(const SolveArgs& a, int dir, const Ti
     }
   } else if (out < nc) {
     double* xp = a.xperm + (int64_t)(tr.first + out) * k;
-    double* xo = a.X + (int64_t)aux.i * a.xrs;
+    double* xo = a.X + (int64_t)__ldg(&a.perm[tr.first + out]) * a.xrs;
 #pragma unroll
     for (int r = 0; r < KT; ++r)
       if (r < k) { xp[r] = acc[r]; xo[(int64_t)r * a.xcs] = acc[r]; }
@@ -339,15 +237,13 @@ __device__ __forceinline__ void tile_store(const SolveArgs& a, int dir, const Ti
 }
 
 template <int KT>
-__global__ void __launch_bounds__(SOLVE_WARPS * 32, 1) solve_kernel(const __grid_constant__ SolveArgs a) {
+__global__ void __launch_bounds__(SOLVE_WARPS * 32, 1) solve_kernel(SolveArgs a) {
   extern __shared__ double smem[];
   __shared__ PhaseRec s_phase[MAX_PHASES_SMEM];
-  __shared__ int s_tab[MAX_SUB_LEVELS];                    // level table of the slot of a subtree phase
+  __shared__ int4 s_next[SOLVE_WARPS][3];                  // first tile record of the next phase, per warp
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double* stage = smem + warp * (32 * KT);                 // [32][KT] per warp
+  double* stage = smem + warp * (32 * KT);                 // [KT][32] per warp
   double* part = smem + SOLVE_WARPS * 32 * KT;             // [SOLVE_WARPS][KT][32] partial sums
-  int4* s_rec = reinterpret_cast<int4*>(smem + 2 * SOLVE_WARPS * 32 * KT);   // tile records, REC_CAP x 48 B
-  int4* s_first = s_rec + 3 * REC_CAP;                     // per warp: first tile record of the next level phase
   unsigned long long target = a.bar_base;
   if (a.times && blockIdx.x == 0 && threadIdx.x == 0) {
     unsigned long long t;
@@ -359,23 +255,13 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32, 1) solve_kernel(const __grid
     int4* dst = reinterpret_cast<int4*>(s_phase);
     for (int e = threadIdx.x; e < 2 * min(a.nphases, MAX_PHASES_SMEM); e += blockDim.x) dst[e] = __ldg(src + e);
   }
-  // ---- pre-phase: permuted copy of the right-hand side (coalesced writes, gathered reads), then a grid barrier
-  {
-    const int k = a.k;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < (int64_t)a.n * k; e += (int64_t)gridDim.x * blockDim.x) {
-      const int64_t i = e / k;
-      const int r = (int)(e - i * k);
-      a.bperm[e] = a.B[(int64_t)__ldg(&a.perm[i]) * a.brs + (int64_t)r * a.bcs];
-    }
-    target += gridDim.x;
-    grid_barrier(a.barrier, target);
-  }
-  bool have_first = false;                                 // s_first[warp] holds this warp's first tile of phase p
+  __syncthreads();
+  bool have_next = false;                                  // s_next[warp] holds this warp's first tile of phase p
   for (int p = 0; p < a.nphases; ++p) {
     const PhaseRec ph = p < MAX_PHASES_SMEM ? s_phase[p] : a.phases[p];
-    const int dir = ph.dir;
-    const bool subtree = ph.ws == 0;
-    const int ws = subtree ? 1 : ph.ws;
+    const int64_t tile_off = ph.tile_off;
+    const int dir = ph.dir, ws = ph.ws, ntiles = ph.ntiles;
+    const bool use_perm = (p == 0);
     // request this warp's first tile record of the NEXT phase now (static schedule): the load completes
     // behind this phase's work instead of in front of the next phase's
     bool nxt_have = false;
@@ -390,85 +276,52 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32, 1) solve_kernel(const __grid
         }
       }
     }
-    // A phase is a sequence of steps; a step is a strided range of tile records [base, end) handled by this
-    // warp group.  Level phase: one step, tiles spread over the grid.  Subtree phase: one step per local
-    // level of the CTA's own subtrees (CTA barrier between steps), tile records staged in shared memory.
-    int nsteps = 1, nrec = 0, tb = 0;
-    const int* tab = nullptr;
-    if (subtree) {
-      nsteps = (int)blockIdx.x < ph.level ? ph.ntiles : 0;   // slots beyond the grid do not exist (nslots == grid)
-      tab = a.sub_ptr + ph.tile_off + (int64_t)blockIdx.x * (ph.ntiles + 1);
-      if (nsteps) {
-        tb = __ldg(&tab[0]);
-        nrec = min(__ldg(&tab[nsteps]) - tb, REC_CAP);
-        if (threadIdx.x <= nsteps && threadIdx.x < MAX_SUB_LEVELS) s_tab[threadIdx.x] = __ldg(&tab[threadIdx.x]);
-        const int4* src = reinterpret_cast<const int4*>(a.tiles + tb);
-        for (int e = threadIdx.x; e < 3 * nrec; e += blockDim.x) s_rec[e] = __ldg(src + e);
-      }
-      __syncthreads();
-      // pull the panels of the slot's fronts into L2 now (one bulk prefetch per front, ~3 - 10 KB each): the
-      // tiles' own loads then see L2 latency, and DRAM streams at full rate instead of in per-tile bursts
-      {
-        const double* pan = dir == 0 ? a.sfwd : a.sbwd;
-        for (int q = threadIdx.x; q < nrec; q += blockDim.x) {
-          const int4 r0 = s_rec[3 * q];
-          if (r0.w == 0) {                                   // first tile of its front
-            const int4 r1 = s_rec[3 * q + 1];
-            const int64_t soff = ((int64_t)(unsigned)r1.x) | ((int64_t)r1.y << 32);
-            prefetch_l2(pan + soff, (unsigned)((r0.y + r0.z) * r0.y) * 8u);
-          }
-        }
+    if (p == 0 && a.nphases > 1) {
+      // permuted copy of the right-hand side for the later phases (coalesced writes, gathered reads)
+      const int k = a.k;
+      for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < (int64_t)a.n * k; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = e / k;
+        const int r = (int)(e - i * k);
+        a.bperm[e] = a.B[(int64_t)__ldg(&a.perm[i]) * a.brs + (int64_t)r * a.bcs];
       }
     }
-    for (int step = 0; step < nsteps; ++step) {
-      int base, stride, end, niter;
-      if (subtree) {
-        const int l = dir == 0 ? step : nsteps - 1 - step;
-        const int t0 = l + 1 < MAX_SUB_LEVELS ? s_tab[l] : __ldg(&tab[l]);
-        end = l + 1 < MAX_SUB_LEVELS ? s_tab[l + 1] : __ldg(&tab[l + 1]);
-        base = t0 + warp;
-        stride = SOLVE_WARPS;
-        niter = (end - t0 + SOLVE_WARPS - 1) / SOLVE_WARPS;
-      } else {
-        const int tpc = SOLVE_WARPS / ws;
-        const int nct = (ph.ntiles + tpc - 1) / tpc;
-        base = (int)ph.tile_off + (int)blockIdx.x * tpc + warp / ws;
-        stride = (int)gridDim.x * tpc;
-        end = (int)ph.tile_off + ph.ntiles;
-        niter = nct > (int)blockIdx.x ? (nct - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    if (ws == 0) {
+      // ---- subtree phase: every slot walks the local levels of its own subtrees; only CTA barriers
+      const int nl = ntiles, nslots = ph.level;
+      for (int slot = blockIdx.x; slot < nslots; slot += gridDim.x) {
+        const int* tab = a.sub_ptr + tile_off + (int64_t)slot * (nl + 1);
+        for (int ll = 0; ll < nl; ++ll) {
+          const int l = dir == 0 ? ll : nl - 1 - ll;
+          const int t0 = __ldg(&tab[l]), t1 = __ldg(&tab[l + 1]);
+          for (int te = t0 + warp; te < t1; te += SOLVE_WARPS) {
+            const TileRec tr = load_tile(a.tiles + te);
+            double acc[KT];
+#pragma unroll
+            for (int r = 0; r < KT; ++r) acc[r] = 0.0;
+            tile_compute<KT>(a, dir, use_perm, tr, lane, 0, 1, stage, acc);
+            tile_store<KT>(a, dir, tr, lane, acc);
+          }
+          __syncthreads();      // CTA-scope ordering: the level's results are visible to the whole slot
+        }
       }
-      const int slice = subtree ? 0 : warp % ws;
-      unsigned long long* dbg = nullptr;
-      if (a.times && blockIdx.x == 0 && warp == 0 && subtree)
-        dbg = a.times + a.nphases + 1 + ((dir * MAX_SUB_LEVELS) + step) * 8;
-      if (dbg && lane == 0) {
-        unsigned long long t;
-        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-        dbg[0] = t;
-        dbg[1] = niter;
-      }
-      for (int it = 0; it < niter; ++it) {
-        long long c0 = 0, c1 = 0;
-        if (dbg) c0 = clock64();
-        const int te = base + it * stride;
-        const bool have = te < end;
+    } else {
+      const int tpc = SOLVE_WARPS / ws;
+      const int sub = warp / ws, slice = warp - sub * ws;
+      const int nct = (ntiles + tpc - 1) / tpc;
+      for (int ct = blockIdx.x; ct < nct; ct += gridDim.x) {
+        const int te = ct * tpc + sub;
+        const bool have = te < ntiles;
         double acc[KT];
 #pragma unroll
         for (int r = 0; r < KT; ++r) acc[r] = 0.0;
         TileRec tr;
         tr.first = tr.nc = tr.nb = tr.tile = 0;
         tr.soff = tr.w_off = tr.row_off = tr.link = 0;
-        TileAux aux;
-        aux.d = 0.0;
-        aux.i = 0;
         if (have) {
-          const int q = te - tb;
-          if (subtree && q < nrec) tr = unpack_tile(s_rec[3 * q], s_rec[3 * q + 1], s_rec[3 * q + 2]);
-          else if (!subtree && it == 0 && have_first) tr = unpack_tile(s_first[3 * warp], s_first[3 * warp + 1], s_first[3 * warp + 2]);
-          else tr = load_tile(a.tiles + te);
-          aux = tile_compute<KT>(a, dir, tr, lane, slice, ws, stage, acc);
+          if (have_next && ct == (int)blockIdx.x) tr = unpack_tile(s_next[warp][0], s_next[warp][1], s_next[warp][2]);
+          else tr = load_tile(a.tiles + tile_off + te);
+          tile_compute<KT>(a, dir, use_perm, tr, lane, slice, ws, stage, acc);
         }
-        if (dbg) c1 = clock64();
         if (ws > 1) {
 #pragma unroll
           for (int r = 0; r < KT; ++r) part[(warp * KT + r) * 32 + lane] = acc[r];
@@ -478,29 +331,14 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32, 1) solve_kernel(const __grid
 #pragma unroll
               for (int r = 0; r < KT; ++r) acc[r] += part[((warp + s) * KT + r) * 32 + lane];
         }
-        if (have && slice == 0) tile_store<KT>(a, dir, tr, lane, aux, acc);
+        if (have && slice == 0) tile_store<KT>(a, dir, tr, lane, acc);
         if (ws > 1) __syncthreads();
-        if (dbg && lane == 0 && it < 3) {
-          dbg[2 + 2 * it] = (unsigned long long)(c1 - c0);
-          dbg[3 + 2 * it] = (unsigned long long)(clock64() - c1);
-        }
       }
-      if (subtree) __syncthreads();     // CTA-scope ordering: the level's results are visible to the whole slot
     }
     // ---- hand the prefetched first tile record of the next phase to the whole warp
-    have_first = nxt_have;
-    if (nxt_have && lane < 3) s_first[3 * warp + lane] = nxt;
+    have_next = nxt_have;
+    if (nxt_have && lane < 3) s_next[warp][lane] = nxt;
     __syncwarp();
-    if (nxt_have) {
-      // ... and pull that tile's panel slice into L2 behind the barrier: after it, the tile's loads see L2 latency
-      const PhaseRec nx = (p + 1) < MAX_PHASES_SMEM ? s_phase[p + 1] : a.phases[p + 1];
-      const TileRec nt = unpack_tile(s_first[3 * warp], s_first[3 * warp + 1], s_first[3 * warp + 2]);
-      const double* M;
-      int ld, c0, c1;
-      tile_range(a, nx.dir, nt, warp % nx.ws, nx.ws, M, ld, c0, c1);
-      const int rows = min(SOLVE_TILE, (nx.dir == 0 ? nt.nc + nt.nb : nt.nc) - nt.tile * SOLVE_TILE);
-      for (int c = c0 + lane; c < c1; c += 32) prefetch_l2(M + (int64_t)c * ld, (unsigned)rows * 8u);
-    }
     target += gridDim.x;
     if (p + 1 < a.nphases) grid_barrier(a.barrier, target);
     if (a.times && blockIdx.x == 0 && threadIdx.x == 0) {
@@ -534,7 +372,7 @@ template <int KT>
 int configure(int slot) {
   KernelCfg& c = g_cfg[slot];
   if (c.ready) return 0;
-  c.smem = (size_t)SOLVE_WARPS * 32 * KT * 8 * 2 + (size_t)(REC_CAP + SOLVE_WARPS) * 48;
+  c.smem = (size_t)SOLVE_WARPS * 32 * KT * 8 * 2;
   EIGD_CUDA(cudaFuncSetAttribute(solve_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
   int occ = 0;
   EIGD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, solve_kernel<KT>, SOLVE_WARPS * 32, c.smem));
@@ -555,7 +393,7 @@ int launch_solve(int slot, eigd_factor* f, SolveArgs& a) {
   EIGD_CUDA(cudaLaunchCooperativeKernel((void*)solve_kernel<KT>, dim3(c.grid), dim3(SOLVE_WARPS * 32), params, c.smem,
                                         g_eigd_stream));
   ++g_eigd_launches;
-  f->bar_base += (unsigned long long)a.nphases * (unsigned long long)c.grid;   // pre-phase + (nphases - 1) barriers
+  f->bar_base += (unsigned long long)(a.nphases - 1) * (unsigned long long)c.grid;
   return 0;
 }
 

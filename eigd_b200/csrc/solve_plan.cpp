@@ -61,20 +61,19 @@ void build_solve_plan_host(const eigd_symbolic* S, int target_warps, int nslots,
   for (int k = 0; k < ns; ++k) P.soff[k + 1] = P.soff[k] + (int64_t)sn_fsize(S, k) * sn_ncols(S, k);
 
   // ---- child slabs and overflow lists ---------------------------------------------------------
-  // the first SOLVE_NSLAB children of a front (ascending order) write their update rows straight into the
-  // parent's rows of their own direct slab; later children keep theirs in the overflow slab and the parent
-  // gathers them
+  // children 0 and 1 of a front (ascending order) write their update rows straight into the parent's
+  // rows of slab 0 / slab 1; later children keep theirs in slab 2 and the parent gathers them
   const int64_t sumf = S->w_off[ns];
   P.slab.assign(ns, 255);
   std::vector<char> has_ovf(ns, 0);
-  std::vector<std::vector<int>> extra;          // per overflow row: sources in the overflow slab
+  std::vector<std::vector<int>> extra;          // per overflow row: sources in slab 2
   std::vector<int64_t> extra_of(sumf, -1);
   for (int p = 0; p < ns; ++p)
     for (int q = S->child_ptr[p]; q < S->child_ptr[p + 1]; ++q) {   // children in ascending order: fixed sum order
       int c = S->child_idx[q];
       int rank = q - S->child_ptr[p];
-      P.slab[c] = rank < SOLVE_NSLAB ? rank : SOLVE_NSLAB;
-      if (rank < SOLVE_NSLAB) continue;
+      P.slab[c] = rank < 2 ? rank : 2;
+      if (rank < 2) continue;
       has_ovf[p] = 1;
       int ncc = sn_ncols(S, c), nbc = sn_nbelow(S, c);
       for (int i = 0; i < nbc; ++i) {
@@ -108,9 +107,7 @@ void build_solve_plan_host(const eigd_symbolic* S, int target_warps, int nslots,
     int p = S->sn_parent[k];
     r.link = (p >= 0 ? S->w_off[p] : 0) | ((int64_t)P.slab[k] << LINK_SLAB_SHIFT);
     if (has_ovf[k]) r.link |= LINK_HAS_OVF;
-    const int nchild = S->child_ptr[k + 1] - S->child_ptr[k];
-    if (nchild > 0) r.link |= LINK_HAS_CHILDREN;
-    r.link |= (int64_t)std::min(nchild, SOLVE_NSLAB) << LINK_NSLAB_SHIFT;
+    if (S->child_ptr[k + 1] > S->child_ptr[k]) r.link |= LINK_HAS_CHILDREN;
     return r;
   };
   // ---- subtree phases: the largest cut whose subtrees still balance over the slots -----------

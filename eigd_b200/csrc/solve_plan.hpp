@@ -12,14 +12,11 @@ constexpr int SOLVE_TILE = 32;    // outputs (front rows / pivot columns) per wa
 
 // link word of a tile record: where the front's update rows go in the forward sweep
 //   bits  0..47  w-row offset of the PARENT front (prefix sum of front sizes)
-//   bits 48..55  slab: 0 .. SOLVE_NSLAB-1 = rank of the front among its siblings (the parent adds its rows of the
-//                direct slabs, no index look-up), SOLVE_NSLAB = a later child (own rows in the overflow slab,
-//                the parent gathers them through the overflow lists), 255 = root (nothing to pass up)
-//   bit  56      the front has children in the overflow slab (its rows consult ovf_row)
-//   bit  57      the front has children at all
-//   bits 58..60  number of direct slabs its children write, min(#children, SOLVE_NSLAB): the others are not read
-constexpr int SOLVE_NSLAB = 4;
-constexpr int LINK_NSLAB_SHIFT = 58;
+//   bits 48..55  slab: 0 / 1 = rank of the front among its siblings (the parent adds slab 0 + slab 1,
+//                no index look-up), 2 = third or later child (own rows in slab 2, the parent
+//                gathers them through the overflow lists), 255 = root (nothing to pass up)
+//   bit  56      the front has children of slab 2 (its rows consult ovf_row)
+//   bit  57      the front has children at all (leaves skip the slab reads)
 constexpr int LINK_SLAB_SHIFT = 48;
 constexpr int64_t LINK_WOFF_MASK = ((int64_t)1 << 48) - 1;
 constexpr int64_t LINK_HAS_OVF = (int64_t)1 << 56;
@@ -54,10 +51,10 @@ static_assert(sizeof(PhaseRec) == 32, "PhaseRec layout");
 struct SolvePlanHost {
   std::vector<int64_t> soff;      // nsuper + 1, prefix sum of f * nc
   // overflow form of the extend-add of the forward sweep (fronts with more than two children):
-  // ovf_row[t] = -1, or the offset o of a list ovf[o] = count, ovf[o+1 ..] = source rows in the overflow slab
+  // ovf_row[t] = -1, or the offset o of a list ovf[o] = count, ovf[o+1 ..] = source rows in slab 2
   std::vector<int> ovf_row;       // sum_front
   std::vector<int> ovf;
-  std::vector<int> slab;          // per supernode: 0 .. SOLVE_NSLAB or 255 (root)
+  std::vector<int> slab;          // per supernode: 0, 1, 2 or 255 (root)
   std::vector<TileRec> tiles;
   std::vector<PhaseRec> phases;   // forward phases (leaves -> root) then backward phases (root -> leaves)
   int nfwd = 0;

@@ -16,7 +16,6 @@ from eigd_b200.device import Symbolic
 import multifrontal_oracle as mo
 
 MASK48 = (1 << 48) - 1
-NSLAB = 4          # direct child slabs (solve_plan.hpp SOLVE_NSLAB)
 
 
 def plan_arrays(sym, target_warps, nslots, cut):
@@ -36,7 +35,7 @@ def emulate(plan, S, sym_arr, dinv, b):
     perm, sn_rows, rel = sym_arr["perm"], sym_arr["sn_rows"], sym_arr["rel"]
     n = len(perm)
     sumf = len(plan["ovf_row"])
-    wbuf = np.zeros((NSLAB + 1, sumf))
+    wbuf = np.zeros((3, sumf))
     bperm = b[perm]
     y, xp = np.zeros(n), np.zeros(n)
     done = set()
@@ -44,12 +43,12 @@ def emulate(plan, S, sym_arr, dinv, b):
     def child(t, link):
         if not (link >> 57) & 1:
             return 0.0
-        v = sum(wbuf[sl, t] for sl in range(min((link >> 58) & 7, NSLAB)))
+        v = wbuf[0, t] + wbuf[1, t]
         if (link >> 56) & 1:
             o = plan["ovf_row"][t]
             if o >= 0:
                 cnt = plan["ovf"][o]
-                v += sum(wbuf[NSLAB, plan["ovf"][o + 1 + q]] for q in range(cnt))
+                v += sum(wbuf[2, plan["ovf"][o + 1 + q]] for q in range(cnt))
         return v
 
     def do_tile(direction, rec):
@@ -72,11 +71,11 @@ def emulate(plan, S, sym_arr, dinv, b):
                     y[first + out] = dinv[first + out] * acc
                 else:
                     slab = (link >> 48) & 0xff
-                    assert slab in range(NSLAB + 1), "a root front has no rows below its pivots"
-                    if slab < NSLAB:
+                    assert slab in (0, 1, 2), "a root front has no rows below its pivots"
+                    if slab < 2:
                         wbuf[slab, (link & MASK48) + rel[row_off + out - nc]] = acc
                     else:
-                        wbuf[NSLAB, w_off + out] = acc
+                        wbuf[2, w_off + out] = acc
         else:
             vec = np.concatenate([y[first:first + nc], xp[sn_rows[row_off:row_off + nb]]])
             for out in range(o0, min(o0 + 32, nc)):
@@ -160,5 +159,5 @@ def test_child_slabs_are_consistent():
     ns = len(par)
     for p in range(ns):
         kids = [c for c in range(ns) if par[c] == p]
-        assert [int(slab[c]) for c in kids] == [min(i, NSLAB) for i in range(len(kids))]
+        assert [int(slab[c]) for c in kids] == [min(i, 2) for i in range(len(kids))]
     assert all(int(slab[k]) == 255 for k in range(ns) if par[k] < 0)

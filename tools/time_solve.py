@@ -42,7 +42,7 @@ import ctypes
 from eigd_b200 import _lib
 lib = _lib.load()
 nph = lib.eigd_solve_num_phases(f.lu.handle)
-buf = torch.zeros(nph + 1 + 2 * 32 * 8, dtype=torch.int64, device="cuda")
+buf = torch.zeros(nph + 1, dtype=torch.int64, device="cuda")
 for k in (1, 10):
     B = torch.randn(n, k, dtype=torch.float64, device="cuda")
     X = torch.empty_like(B)
@@ -53,10 +53,4 @@ for k in (1, 10):
         t = buf.cpu().numpy()[: nph + 1]
         if it: acc += np.diff(t) / 4.0
     lib.eigd_solve_set_phase_times(None)
-    d = buf.cpu().numpy()[nph + 1:].reshape(2, 32, 8)
-    for dr in range(2):
-        for st in range(6):
-            r = d[dr, st]
-            if r[0]:
-                print("   dir %d step %d  start +%.1f us  niter %d  first tiles (compute, store) cycles: %s" % (dr, st, (r[0] - t[0]) / 1e3, r[1], r[2:8]))
     print("k=%d phase us:" % k, " ".join("%.1f" % (v / 1e3) for v in acc), " total %.1f" % (acc.sum() / 1e3))
