@@ -387,14 +387,17 @@ def run_ours(args, rank, world):
                 "note": "reference-facing numpy API: host scipy K, M, K - sigma*M (values; the shared int32 pattern is uploaded once "
                         "per mesh), host Phib in; host lam, Phi, psi, dfdx out; pageable host memory"},
         "stages_s": stage, "per_step_ms": per_step_ms,
-        "roofline": {"bound": "hbm", "kernel": "solve_kernel<%d>: multifrontal LDL^T triangular solve, forward + backward sweep, "
-                                               "%d right-hand side(s), one persistent cooperative launch" % (kdom, kdom),
+        "roofline": {"bound": "hbm", "kernel": "multifrontal LDL^T triangular solve, forward + backward sweep, %d right-hand side(s): "
+                                               "subtree_kernel<%d> (forward, TMA-staged fronts) + solve_kernel<%d> (persistent cooperative "
+                                               "level phases) + subtree_kernel<%d> (backward); 'launch' below = one such solve call"
+                                               % (kdom, kdom, kdom, kdom),
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                      "traffic": traffic, "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"],
                      "launches_per_step": dom["launches_per_step"], "ms_per_launch": dom["ms_per_launch"],
                      "share_of_step": tot_ms / (ms * args.steps) if ms else None,
-                     "note": "latency-bound: 2 subtree phases + 22 level phases separated by grid barriers (DESIGN.md section 5)",
+                     "note": "issue/latency-bound, not DRAM-bound: 2 subtree phases (front mode) + 22 level phases separated by grid barriers "
+                             "(DESIGN.md section 5 has the ablation)",
                      "by_rhs": by_rhs},
         "timeline_ms_per_step": {k: v["ms"] / args.steps for k, v in tl.items()},
         "counts": {"eig_solves": model.profile["solve preconditioner count"],

@@ -64,7 +64,7 @@ int build_symdev(eigd_symbolic* S) {
   h->linv_total = linv_off[ns];
   std::vector<int64_t> soff(ns + 1, 0), xoff(ns + 1, 0);
   for (int k = 0; k < ns; ++k) {
-    soff[k + 1] = soff[k] + (int64_t)sn_fsize(S, k) * sn_ncols(S, k);
+    soff[k + 1] = soff[k] + solve_panel_doubles(sn_fsize(S, k), sn_ncols(S, k));
     xoff[k + 1] = xoff[k] + (int64_t)sn_ncols(S, k) * sn_ncols(S, k);
   }
   h->panel_total = soff[ns];

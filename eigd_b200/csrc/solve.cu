@@ -23,11 +23,13 @@
 #include "../../include/eigd_b200.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 namespace {
 
 constexpr int MAX_PHASES_SMEM = 96;
+constexpr int MAX_SUB_LEVELS = 32;
 
 struct SolveArgs {
   const TileRec* tiles;
@@ -55,6 +57,10 @@ struct SolveArgs {
   int n, k;
   unsigned long long* barrier;
   unsigned long long bar_base;
+  int dbg;                        // developer ablation (EIGD_SOLVE_DBG): bit 0 no operand loads, bit 1 no panel copies, bit 2 no stores
+  int p_begin, p_end;             // phases run by the cooperative kernel
+  int ring_w;                     // bytes of shared-memory panel buffer per warp (front mode of the subtree phases)
+  int rec_cap;                    // tile records of a slot that fit in shared memory
   unsigned long long* times;      // developer profiling: %globaltimer of CTA 0 after every phase (NULL: off)
 };
 
@@ -66,6 +72,21 @@ __device__ __forceinline__ void add_row(const double* __restrict__ base, int64_t
 #pragma unroll
   for (int r = 0; r < KT; ++r)
     if (r < k) v[r] += __ldcg(p + r);
+}
+
+// v += the updates addressed to w-row t by third and later children (overflow slab), via the row's source list
+template <int KT>
+__device__ __forceinline__ void ovf_add(const SolveArgs& a, int64_t t, double* v) {
+  const int o = __ldg(&a.ovf_row[t]);
+  if (o < 0) return;
+  const int cnt = __ldg(&a.ovf[o]);
+  const double* p2 = a.wbuf + 2 * a.slab_stride;
+  for (int q = 0; q < cnt; ++q) {
+    const int64_t src = __ldg(&a.ovf[o + 1 + q]);
+#pragma unroll
+    for (int r = 0; r < KT; ++r)
+      if (r < a.k) v[r] += __ldcg(p2 + (int64_t)r * a.sumf + src);
+  }
 }
 
 // v += the forward-sweep updates addressed to w-row t: slab 0 + slab 1 (+ overflow list), fixed order
@@ -113,10 +134,14 @@ __device__ __forceinline__ TileRec load_tile(const TileRec* p) {
 // instruction stream, not from occupancy: the panel entries of a sub-chunk are requested back to back
 // (MC independent 8-byte loads per lane, 256 B per warp each) BEFORE the gather of the input vector, so
 // one DRAM round trip covers MC columns.
-template <int KT, class StageFn>
+template <int KT>
+struct DefaultMC {
+  static constexpr int value = KT <= 2 ? 32 : (KT <= 10 ? 16 : 8);
+};
+
+template <int KT, int MC, class StageFn>
 __device__ __forceinline__ void warp_panel_product(const double* __restrict__ M, int64_t ld, int c0, int c1, int lane,
                                                    double* stage, double* acc, StageFn stage_fn) {
-  constexpr int MC = KT <= 2 ? 32 : (KT <= 10 ? 16 : 8);
   constexpr int g = 0, nks = 1;
   for (int cc = c0; cc < c1; cc += 32) {
     const int ncol = min(32, c1 - cc);
@@ -165,7 +190,7 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* ctr, unsigned l
 // the products of one warp tile: slice `slice` of `ws` of the reduction dimension.
 // use_perm: the right-hand side is gathered from B through perm (first phase; later phases read the
 // permuted copy written during the first one)
-template <int KT>
+template <int KT, int MC = DefaultMC<KT>::value>
 __device__ __forceinline__ void tile_compute(const SolveArgs& a, int dir, bool use_perm, const TileRec& tr, int lane,
                                              int slice, int ws, double* stage, double* acc) {
   constexpr int to = SOLVE_TILE;
@@ -180,7 +205,7 @@ __device__ __forceinline__ void tile_compute(const SolveArgs& a, int dir, bool u
     const int per = (cend + ws - 1) / ws;
     const int c0 = slice * per, c1 = min(cend, c0 + per);
     const double* M = a.sfwd + tr.soff + min(out, f - 1);
-    warp_panel_product<KT>(M, f, c0, c1, lane, stage, acc, [&](int c, double* v) {
+    warp_panel_product<KT, MC>(M, f, c0, c1, lane, stage, acc, [&](int c, double* v) {
       if (use_perm) {
         const int64_t po = __ldg(&a.perm[tr.first + c]);
         const double* bp = a.B + po * a.brs;
@@ -198,7 +223,7 @@ __device__ __forceinline__ void tile_compute(const SolveArgs& a, int dir, bool u
     const int per = (len + ws - 1) / ws;
     const int i0 = o0 + slice * per, i1 = min(f, i0 + per);
     const double* M = a.sbwd + tr.soff + min(out, nc - 1);
-    warp_panel_product<KT>(M, nc, i0, i1, lane, stage, acc, [&](int i, double* v) {
+    warp_panel_product<KT, MC>(M, nc, i0, i1, lane, stage, acc, [&](int i, double* v) {
       if (i < nc) add_row<KT>(a.ybuf, tr.first + i, k, v);
       else add_row<KT>(a.xperm, __ldg(&a.sn_rows[tr.row_off + i - nc]), k, v);
     });
@@ -236,6 +261,430 @@ __device__ __forceinline__ void tile_store(const SolveArgs& a, int dir, const Ti
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// FRONT MODE of the subtree phases.  Below the cut the fronts are small (nc ~ 4 - 30 pivot columns, f ~ 20 - 110
+// rows: a 2 - 10 KB panel) and there are thousands of them per SM; with one warp tile per 32 outputs the solve
+// was bound by the load/store path (every lane fetching 8 bytes of panel per instruction, all 16 warps at
+// once) and by per-tile overhead, not by DRAM.  Here the unit of work is a FRONT: lane 0
+// of the warp brings the whole panel -- one contiguous, 16-byte aligned run of f x nc doubles -- into the warp's
+// shared-memory buffer with ONE bulk copy (cp.async.bulk, completion on an mbarrier), the next front's panel is
+// requested before the current one is consumed (two half-buffers), the operand vector is gathered once per
+// front instead of once per tile, and all row tiles run out of shared memory.  Fronts that do not fit (panel
+// larger than the warp's buffer, or more than 32 pivot columns) take the tile path below, record by record.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+  } while (!ok);
+}
+
+struct FrontRing {
+  char* base;                  // this warp's buffer: two half-buffers of `half` bytes
+  int half;
+  unsigned long long* bar;     // two mbarriers, one per half (a front larger than `half` uses both halves and bar[0])
+  unsigned uses[2];            // completed copies per barrier (parity of the next wait)
+};
+
+constexpr int FRONT_RT = 3;    // row tiles (forward) / row chunks (backward) a pipelined front may have: f <= 96
+
+// Operands of one front, REQUESTED one front ahead (software pipeline in registers, KT <= 2): by the time the
+// front is processed its loads have landed, so a front costs no exposed memory round trip in the forward sweep
+// and one (index -> value) in the backward sweep.
+template <int KT>
+struct FrontOps {
+  double b[KT], s0[KT], s1[KT];            // forward: w1 entry of lane c = b + (s0 + s1)
+  double u0[FRONT_RT][KT], u1[FRONT_RT][KT];   // forward: children's updates of row t*32 + lane
+  double auxd[FRONT_RT];                   // forward: D^-1 of pivot row t*32 + lane
+  int auxi[FRONT_RT];                      // forward: position of update row t*32 + lane in the parent; backward:
+                                           // row index of input entry t*32 + lane (auxi[t]) ...
+  int perm0;                               // ... backward: original index of pivot column `lane`
+};
+
+template <int KT>
+__device__ __forceinline__ void front_request(const SolveArgs& a, int dir, bool use_perm, const TileRec& tr, int lane,
+                                              FrontOps<KT>& o) {
+  const int k = a.k;
+  const int nc = tr.nc, f = tr.nc + tr.nb;
+  const bool kids = (tr.link & LINK_HAS_CHILDREN) != 0;
+  if (a.dbg & 1) {
+#pragma unroll
+    for (int r = 0; r < KT; ++r) o.b[r] = o.s0[r] = o.s1[r] = 1.0;
+#pragma unroll
+    for (int t = 0; t < FRONT_RT; ++t) {
+      o.auxd[t] = 1.0;
+      o.auxi[t] = 0;
+#pragma unroll
+      for (int r = 0; r < KT; ++r) o.u0[t][r] = o.u1[t][r] = 0.0;
+    }
+    o.perm0 = 0;
+    return;
+  }
+  if (dir == 0) {
+    const int64_t col = tr.first + min(lane, nc - 1);
+    const double* bp = use_perm ? a.B + (int64_t)__ldg(&a.perm[col]) * a.brs : a.bperm + col * k;
+    const int64_t bs = use_perm ? a.bcs : 1;
+    const double* w0 = a.wbuf + tr.w_off + lane;
+#pragma unroll
+    for (int r = 0; r < KT; ++r) {
+      const bool ok = r < k && lane < nc;
+      o.b[r] = ok ? __ldcg(bp + r * bs) : 0.0;
+      o.s0[r] = (ok && kids) ? __ldcg(w0 + (int64_t)r * a.sumf) : 0.0;
+      o.s1[r] = (ok && kids) ? __ldcg(w0 + a.slab_stride + (int64_t)r * a.sumf) : 0.0;
+    }
+#pragma unroll
+    for (int t = 0; t < FRONT_RT; ++t) {
+      const int row = t * SOLVE_TILE + lane;
+      o.auxd[t] = row < nc ? __ldg(&a.dinv[tr.first + row]) : 0.0;
+      o.auxi[t] = (row >= nc && row < f) ? __ldg(&a.rel[tr.row_off + row - nc]) : 0;
+#pragma unroll
+      for (int r = 0; r < KT; ++r) {
+        const bool ok = r < k && kids && row >= nc && row < f;
+        o.u0[t][r] = ok ? __ldcg(w0 + t * SOLVE_TILE + (int64_t)r * a.sumf) : 0.0;
+        o.u1[t][r] = ok ? __ldcg(w0 + t * SOLVE_TILE + a.slab_stride + (int64_t)r * a.sumf) : 0.0;
+      }
+    }
+  } else {
+    o.perm0 = lane < nc ? __ldg(&a.perm[tr.first + lane]) : 0;
+#pragma unroll
+    for (int t = 0; t < FRONT_RT; ++t) {
+      const int i = t * SOLVE_TILE + lane;
+      o.auxi[t] = i < nc ? tr.first + i : (i < f ? __ldg(&a.sn_rows[tr.row_off + i - nc]) : 0);
+    }
+  }
+}
+
+// one front out of shared memory (buf = its panel, copy completion on `bar`); ops = its prefetched operands (PIPE)
+template <int KT, bool PIPE>
+__device__ __forceinline__ void front_compute(const SolveArgs& a, int dir, bool use_perm, TileRec tr, const double* buf,
+                                              unsigned long long* bar, unsigned parity, const FrontOps<PIPE ? KT : 1>& ops,
+                                              int lane, double* stage) {
+  const int k = a.k;
+  const int nc = tr.nc, f = tr.nc + tr.nb;
+    const int ntile = (f + SOLVE_TILE - 1) / SOLVE_TILE;
+    if (dir == 0) {
+      // ---- forward: w1 (nc <= 32 entries) gathered once, then every row tile of S w1 out of shared memory
+      double v[KT];
+      if constexpr (PIPE) {
+#pragma unroll
+        for (int r = 0; r < KT; ++r) v[r] = ops.b[r] + (ops.s0[r] + ops.s1[r]);
+        if ((tr.link & LINK_HAS_OVF) && lane < nc) {
+          double z[KT];
+#pragma unroll
+          for (int r = 0; r < KT; ++r) z[r] = 0.0;
+          ovf_add<KT>(a, tr.w_off + lane, z);
+#pragma unroll
+          for (int r = 0; r < KT; ++r) v[r] += z[r];
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < KT; ++r) v[r] = 0.0;
+        if (lane < nc) {
+          if (use_perm) {
+            const double* bp = a.B + (int64_t)__ldg(&a.perm[tr.first + lane]) * a.brs;
+#pragma unroll
+            for (int r = 0; r < KT; ++r)
+              if (r < k) v[r] = bp[(int64_t)r * a.bcs];
+          } else {
+            add_row<KT>(a.bperm, tr.first + lane, k, v);
+          }
+          child_add<KT>(a, tr.w_off + lane, tr.link, v);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < KT; ++r) stage[r * 32 + lane] = v[r];
+      __syncwarp();
+      if (!(a.dbg & 2)) mbar_wait(bar, parity);
+#pragma unroll
+      for (int t = 0; t < (PIPE ? FRONT_RT : 8); ++t) {
+        if (t >= ntile) break;
+        const int row = t * SOLVE_TILE + lane;
+        double acc[KT];
+#pragma unroll
+        for (int r = 0; r < KT; ++r) acc[r] = 0.0;
+        if constexpr (!PIPE) {
+          if (row >= nc && row < f) child_add<KT>(a, tr.w_off + row, tr.link, acc);
+        }
+        const int cend = min(nc, (t + 1) * SOLVE_TILE);
+        const double* col = buf + min(row, f - 1);
+#pragma unroll 4
+        for (int c = 0; c < cend; ++c) {
+          const double m = col[c * f];
+#pragma unroll
+          for (int r = 0; r < KT; ++r) acc[r] = fma(m, stage[r * 32 + c], acc[r]);
+        }
+        if constexpr (PIPE) {
+#pragma unroll
+          for (int r = 0; r < KT; ++r) acc[r] += ops.u0[t][r] + ops.u1[t][r];
+          if ((tr.link & LINK_HAS_OVF) && row >= nc && row < f) ovf_add<KT>(a, tr.w_off + row, acc);
+          // store with the prefetched D^-1 / parent position (tile_store without its look-up)
+          if (a.dbg & 4) {
+          } else if (row < nc) {
+            double* y = a.ybuf + (int64_t)(tr.first + row) * k;
+#pragma unroll
+            for (int r = 0; r < KT; ++r)
+              if (r < k) y[r] = ops.auxd[t] * acc[r];
+          } else if (row < f) {
+            const int sl = (int)((tr.link >> LINK_SLAB_SHIFT) & 0xff);
+            const int64_t dst = sl < 2 ? sl * a.slab_stride + (tr.link & LINK_WOFF_MASK) + ops.auxi[t]
+                                       : 2 * a.slab_stride + tr.w_off + row;
+            double* w = a.wbuf + dst;
+#pragma unroll
+            for (int r = 0; r < KT; ++r)
+              if (r < k) w[(int64_t)r * a.sumf] = acc[r];
+          }
+        } else {
+          tr.tile = t;
+          tile_store<KT>(a, 0, tr, lane, acc);
+        }
+      }
+    } else {
+      // ---- backward: x1 = S^T [z1 ; x2], lane = pivot column (nc <= 32), front rows streamed in chunks of 32
+      double vv[PIPE ? FRONT_RT : 1][KT];
+      if constexpr (PIPE) {
+        // all chunks' values are requested at once (their indices arrived with the previous front)
+#pragma unroll
+        for (int t = 0; t < FRONT_RT; ++t) {
+          const int i = t * SOLVE_TILE + lane;
+          const double* src = (i < nc ? a.ybuf : a.xperm) + (int64_t)ops.auxi[t] * k;
+#pragma unroll
+          for (int r = 0; r < KT; ++r) vv[t][r] = (i < f && r < k) ? __ldcg(src + r) : 0.0;
+        }
+      }
+      if (!(a.dbg & 2)) mbar_wait(bar, parity);
+      double acc[KT];
+#pragma unroll
+      for (int r = 0; r < KT; ++r) acc[r] = 0.0;
+      const double* colp = buf + min(lane, nc - 1);
+#pragma unroll
+      for (int t = 0; t < (PIPE ? FRONT_RT : 8); ++t) {
+        const int cc = t * SOLVE_TILE;
+        if (cc >= f) break;
+        const int nrow = min(32, f - cc);
+        if constexpr (PIPE) {
+#pragma unroll
+          for (int r = 0; r < KT; ++r) stage[r * 32 + lane] = vv[t][r];
+        } else {
+          double v[KT];
+#pragma unroll
+          for (int r = 0; r < KT; ++r) v[r] = 0.0;
+          if (lane < nrow) {
+            const int i = cc + lane;
+            if (i < nc) add_row<KT>(a.ybuf, tr.first + i, k, v);
+            else add_row<KT>(a.xperm, __ldg(&a.sn_rows[tr.row_off + i - nc]), k, v);
+          }
+#pragma unroll
+          for (int r = 0; r < KT; ++r) stage[r * 32 + lane] = v[r];
+        }
+        __syncwarp();
+        const double* rowp = colp + cc * nc;
+#pragma unroll 4
+        for (int j = 0; j < nrow; ++j) {
+          const double m = rowp[j * nc];
+#pragma unroll
+          for (int r = 0; r < KT; ++r) acc[r] = fma(m, stage[r * 32 + j], acc[r]);
+        }
+        __syncwarp();
+      }
+      if constexpr (PIPE) {
+        if (lane < nc && !(a.dbg & 4)) {
+          double* xp = a.xperm + (int64_t)(tr.first + lane) * k;
+          double* xo = a.X + (int64_t)ops.perm0 * a.xrs;
+#pragma unroll
+          for (int r = 0; r < KT; ++r)
+            if (r < k) { xp[r] = acc[r]; xo[(int64_t)r * a.xcs] = acc[r]; }
+        }
+      } else {
+        tr.tile = 0;
+        tile_store<KT>(a, 1, tr, lane, acc);
+      }
+    }
+}
+
+constexpr int FRONT_DEPTH = 2;   // panel copies in flight per warp
+
+// Every front of this CTA's slot that belongs to this warp (front te = T0(level) + warp + 16 j), level by level
+// with a CTA barrier between levels.  The PANEL copies run ahead of the computation by up to FRONT_DEPTH fronts
+// and across level boundaries (panels do not depend on computed data): a FIFO of variable-size allocations in the
+// warp's ring buffer, one mbarrier per FIFO position.  The OPERANDS (right-hand side, child updates, D^-1, row
+// positions) are requested one front ahead into registers (KT <= 2).
+template <int KT>
+__device__ __forceinline__ void fronts_phase(const SolveArgs& a, int dir, bool use_perm, int nl, const int* s_tab, int tb,
+                                             int nrec, const int4* s_rec, int lane, int warp, double* stage, char* ring,
+                                             int ring_w, unsigned long long* bars, int* s_q) {
+  constexpr bool PIPE = KT == 1;
+  // the backward sweep of a multi-column solve is faster on the tile path (measured: k = 10, 95 vs 103 us at C2)
+  const bool front_ok = dir == 0 || KT == 1;
+  const double* panels = dir == 0 ? a.sfwd : a.sbwd;
+  auto record = [&](int te) {
+    const int q = te - tb;
+    return q < nrec ? unpack_tile(s_rec[3 * q], s_rec[3 * q + 1], s_rec[3 * q + 2]) : load_tile(a.tiles + te);
+  };
+  auto fits = [&](const TileRec& t, unsigned b) {
+    return front_ok && t.nc <= 32 && (int)b <= ring_w && (!PIPE || t.nc + t.nb <= FRONT_RT * SOLVE_TILE);
+  };
+  auto level_of = [&](int ll) { return dir == 0 ? ll : nl - 1 - ll; };
+  // producer cursor (pl, pte): next front whose panel copy has not been requested yet
+  int pl = 0, pte = s_tab[level_of(0)] + warp;
+  auto p_skip = [&]() {           // move the producer cursor to a valid front or to the end (pl == nl)
+    while (pl < nl && pte >= s_tab[level_of(pl) + 1]) {
+      ++pl;
+      if (pl < nl) pte = s_tab[level_of(pl)] + warp;
+    }
+  };
+  p_skip();
+  int qh = 0, qn = 0;             // FIFO head position and occupancy; entry e: s_q[2e] = offset (-1: no copy), s_q[2e+1] = bytes
+  unsigned par = 0;               // parity bit per FIFO position
+  int last_end = 0;               // end of the newest allocation
+  auto produce = [&]() {
+    while (qn < FRONT_DEPTH && pl < nl) {
+      const TileRec t = record(pte);
+      const unsigned b = (unsigned)solve_panel_doubles(t.nc + t.nb, t.nc) * 8u;
+      const int e = (qh + qn) % FRONT_DEPTH;
+      int off = -1;
+      if (fits(t, b)) {
+        off = (last_end + 127) & ~127;
+        if (off + (int)b > ring_w) off = 0;
+        bool clash = false;
+        for (int i = 0; i < qn; ++i) {
+          const int ei = (qh + i) % FRONT_DEPTH;
+          const int o = s_q[2 * ei], l = s_q[2 * ei + 1];
+          if (o >= 0 && off < o + l && o < off + (int)b) clash = true;
+        }
+        if (clash) return;         // no room yet: try again after the next front has been consumed
+        if (lane == 0 && !(a.dbg & 2)) bulk_load(ring + off, panels + t.soff, b, &bars[e]);
+        last_end = off + (int)b;
+      }
+      __syncwarp();
+      if (lane == 0) { s_q[2 * e] = off; s_q[2 * e + 1] = (int)b; }
+      __syncwarp();
+      ++qn;
+      pte += SOLVE_WARPS;
+      p_skip();
+    }
+  };
+  produce();
+  FrontOps<PIPE ? KT : 1> ops, nops;
+  bool ops_ready = false;
+  for (int ll = 0; ll < nl; ++ll) {
+    const int l = level_of(ll);
+    const int t0 = s_tab[l], t1 = s_tab[l + 1];
+    for (int te = t0 + warp; te < t1; te += SOLVE_WARPS) {
+      TileRec tr = record(te);
+      const int off = s_q[2 * qh];
+      const unsigned parity = (par >> qh) & 1u;
+      if constexpr (PIPE) {
+        if (off >= 0 && !ops_ready) front_request<KT>(a, dir, use_perm, tr, lane, ops);
+      }
+      bool nops_ready = false;
+      if constexpr (PIPE) {
+        // operands of this warp's next front of the SAME level (the next level's depend on this level's results)
+        if (te + SOLVE_WARPS < t1) {
+          const TileRec nt = record(te + SOLVE_WARPS);
+          if (fits(nt, (unsigned)solve_panel_doubles(nt.nc + nt.nb, nt.nc) * 8u)) {
+            front_request<KT>(a, dir, use_perm, nt, lane, nops);
+            nops_ready = true;
+          }
+        }
+      }
+      if (off < 0) {
+        // ---- tile path (global loads), every 32-output tile of the front
+        const int nc = tr.nc, f = tr.nc + tr.nb;
+        const int ntile = ((dir == 0 ? f : nc) + SOLVE_TILE - 1) / SOLVE_TILE;
+        for (int t = 0; t < ntile; ++t) {
+          tr.tile = t;
+          double acc[KT];
+#pragma unroll
+          for (int r = 0; r < KT; ++r) acc[r] = 0.0;
+          tile_compute<KT, (KT <= 2 ? 8 : DefaultMC<KT>::value)>(a, dir, use_perm, tr, lane, 0, 1, stage, acc);
+          tile_store<KT>(a, dir, tr, lane, acc);
+        }
+      } else {
+        front_compute<KT, PIPE>(a, dir, use_perm, tr, reinterpret_cast<const double*>(ring + off), &bars[qh], parity, ops,
+                                lane, stage);
+        par ^= 1u << qh;
+      }
+      __syncwarp();               // every lane is done with the allocation before it can be reused
+      qh = (qh + 1) % FRONT_DEPTH;
+      --qn;
+      produce();
+      if constexpr (PIPE) {
+        ops = nops;
+        ops_ready = nops_ready;
+      }
+    }
+    ops_ready = false;
+    __syncthreads();              // CTA-scope ordering: the level's results are visible to the whole slot
+  }
+}
+
+// A subtree phase in FRONT MODE as its own (ordinary, non-cooperative) launch: one CTA per slot.  The forward one
+// is the first thing a solve does, the backward one the last, so stream order replaces the grid barrier; the kernel
+// gets its own register / shared-memory budget (panel ring) and the level kernel keeps its L1.
+template <int KT>
+__global__ void __launch_bounds__(SOLVE_WARPS * 32, 1) subtree_kernel(SolveArgs a, int p) {
+  extern __shared__ double smem[];
+  __shared__ int s_tab[MAX_SUB_LEVELS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* stage = smem + warp * (32 * KT);                 // [KT][32] per warp
+  char* ring_all = reinterpret_cast<char*>(smem + SOLVE_WARPS * 32 * KT);
+  unsigned long long* mbar_all = reinterpret_cast<unsigned long long*>(ring_all + (size_t)SOLVE_WARPS * a.ring_w);
+  int* s_q = reinterpret_cast<int*>(mbar_all + FRONT_DEPTH * SOLVE_WARPS) + 2 * FRONT_DEPTH * warp;
+  int4* s_rec = reinterpret_cast<int4*>(mbar_all + 2 * FRONT_DEPTH * SOLVE_WARPS);
+  unsigned long long* bars = mbar_all + FRONT_DEPTH * warp;
+  if (lane < FRONT_DEPTH) mbar_init(&bars[lane], 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  const PhaseRec ph = a.phases[p];
+  const int dir = ph.dir, nl = ph.ntiles, nslots = ph.level;
+  const bool use_perm = (p == 0);
+  if (a.times && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    a.times[p] = t;
+  }
+  for (int slot = blockIdx.x; slot < nslots; slot += gridDim.x) {
+    const int* tab = a.sub_ptr + ph.tile_off + (int64_t)slot * (nl + 1);
+    const int tb = __ldg(&tab[0]);
+    const int nrec = min(__ldg(&tab[nl]) - tb, a.rec_cap);
+    __syncthreads();
+    if (threadIdx.x <= nl && threadIdx.x < MAX_SUB_LEVELS) s_tab[threadIdx.x] = __ldg(&tab[threadIdx.x]);
+    {
+      const int4* src = reinterpret_cast<const int4*>(a.tiles + tb);
+      for (int e = threadIdx.x; e < 3 * nrec; e += blockDim.x) s_rec[e] = __ldg(src + e);
+    }
+    __syncthreads();
+    fronts_phase<KT>(a, dir, use_perm, nl, s_tab, tb, nrec, s_rec, lane, warp, stage, ring_all + (size_t)warp * a.ring_w,
+                     a.ring_w, bars, s_q);
+  }
+  if (use_perm) {
+    // permuted copy of the right-hand side for the level phases (coalesced writes, gathered reads)
+    const int k = a.k;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < (int64_t)a.n * k; e += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t i = e / k;
+      const int r = (int)(e - i * k);
+      a.bperm[e] = a.B[(int64_t)__ldg(&a.perm[i]) * a.brs + (int64_t)r * a.bcs];
+    }
+  }
+  if (a.times && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    a.times[p + 1] = t;
+  }
+}
+
+// The phases [a.p_begin, a.p_end) as one persistent cooperative kernel, a grid barrier between consecutive phases.
 template <int KT>
 __global__ void __launch_bounds__(SOLVE_WARPS * 32, 1) solve_kernel(SolveArgs a) {
   extern __shared__ double smem[];
@@ -245,7 +694,7 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32, 1) solve_kernel(SolveArgs a)
   double* stage = smem + warp * (32 * KT);                 // [KT][32] per warp
   double* part = smem + SOLVE_WARPS * 32 * KT;             // [SOLVE_WARPS][KT][32] partial sums
   unsigned long long target = a.bar_base;
-  if (a.times && blockIdx.x == 0 && threadIdx.x == 0) {
+  if (a.times && blockIdx.x == 0 && threadIdx.x == 0 && a.p_begin == 0) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     a.times[0] = t;
@@ -257,7 +706,7 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32, 1) solve_kernel(SolveArgs a)
   }
   __syncthreads();
   bool have_next = false;                                  // s_next[warp] holds this warp's first tile of phase p
-  for (int p = 0; p < a.nphases; ++p) {
+  for (int p = a.p_begin; p < a.p_end; ++p) {
     const PhaseRec ph = p < MAX_PHASES_SMEM ? s_phase[p] : a.phases[p];
     const int64_t tile_off = ph.tile_off;
     const int dir = ph.dir, ws = ph.ws, ntiles = ph.ntiles;
@@ -266,7 +715,7 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32, 1) solve_kernel(SolveArgs a)
     // behind this phase's work instead of in front of the next phase's
     bool nxt_have = false;
     int4 nxt = make_int4(0, 0, 0, 0);
-    if (p + 1 < a.nphases) {
+    if (p + 1 < a.p_end) {
       const PhaseRec nx = (p + 1) < MAX_PHASES_SMEM ? s_phase[p + 1] : a.phases[p + 1];
       if (nx.ws > 0) {
         const int te = (int)blockIdx.x * (SOLVE_WARPS / nx.ws) + warp / nx.ws;
@@ -276,7 +725,7 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32, 1) solve_kernel(SolveArgs a)
         }
       }
     }
-    if (p == 0 && a.nphases > 1) {
+    if (p == 0 && a.p_end > 1) {
       // permuted copy of the right-hand side for the later phases (coalesced writes, gathered reads)
       const int k = a.k;
       for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < (int64_t)a.n * k; e += (int64_t)gridDim.x * blockDim.x) {
@@ -340,7 +789,7 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32, 1) solve_kernel(SolveArgs a)
     if (nxt_have && lane < 3) s_next[warp][lane] = nxt;
     __syncwarp();
     target += gridDim.x;
-    if (p + 1 < a.nphases) grid_barrier(a.barrier, target);
+    if (p + 1 < a.p_end) grid_barrier(a.barrier, target);
     if (a.times && blockIdx.x == 0 && threadIdx.x == 0) {
       unsigned long long t;
       asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -363,7 +812,10 @@ int upload_vec(SymDevHolder* h, const std::vector<T>& v, T** out) {
 struct KernelCfg {
   bool ready = false;
   int grid = 0;
-  size_t smem = 0;
+  size_t smem = 0;      // cooperative level kernel: staging + partial sums
+  size_t smem_sub = 0;  // subtree kernel: staging + panel ring + mbarriers + front records
+  int ring_w = 0;       // panel ring bytes per warp
+  int rec_cap = 0;      // front records staged in shared memory
 };
 KernelCfg g_cfg[8];
 int g_num_sms = 0;
@@ -372,11 +824,20 @@ template <int KT>
 int configure(int slot) {
   KernelCfg& c = g_cfg[slot];
   if (c.ready) return 0;
-  c.smem = (size_t)SOLVE_WARPS * 32 * KT * 8 * 2;
+  const size_t stage_b = (size_t)SOLVE_WARPS * 32 * KT * 8;
+  c.smem = 2 * stage_b;
   EIGD_CUDA(cudaFuncSetAttribute(solve_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
   int occ = 0;
   EIGD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, solve_kernel<KT>, SOLVE_WARPS * 32, c.smem));
   if (occ < 1) { eigd_set_error("solve: kernel does not fit on an SM"); return 5; }
+  // subtree kernel: staging [16][KT][32] | panel ring | 32 mbarriers | front records; 227 KB per CTA on sm_100a
+  const size_t budget = 227 * 1024 - 1024;
+  c.rec_cap = KT <= 4 ? 512 : 256;
+  size_t ring = (budget - stage_b - 2 * FRONT_DEPTH * SOLVE_WARPS * 8 - (size_t)c.rec_cap * 48) / SOLVE_WARPS;
+  ring = std::min<size_t>(ring, 10240) / 256 * 256;
+  c.ring_w = (int)ring;
+  c.smem_sub = stage_b + ring * SOLVE_WARPS + 2 * FRONT_DEPTH * SOLVE_WARPS * 8 + (size_t)c.rec_cap * 48;
+  EIGD_CUDA(cudaFuncSetAttribute(subtree_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem_sub));
   c.grid = g_num_sms;
   c.ready = true;
   return 0;
@@ -387,13 +848,34 @@ int launch_solve(int slot, eigd_factor* f, SolveArgs& a) {
   int rc = configure<KT>(slot);
   if (rc) return rc;
   const KernelCfg& c = g_cfg[slot];
+  const std::vector<PhaseRec>& hp = f->h->solve.host_phases;
+  const int np = a.nphases;
   a.barrier = f->barrier;
+  a.ring_w = c.ring_w;
+  a.rec_cap = c.rec_cap;
+  // subtree phases in front mode run as their own launches in front of / behind the cooperative level kernel
+  const bool sub_first = np >= 1 && hp[0].ws == 0 && hp[0].pad == 0;
+  const bool sub_last = np >= 2 && hp[np - 1].ws == 0 && hp[np - 1].pad == 0;
+  a.p_begin = sub_first ? 1 : 0;
+  a.p_end = sub_last ? np - 1 : np;
   a.bar_base = f->bar_base;
-  void* params[] = {(void*)&a};
-  EIGD_CUDA(cudaLaunchCooperativeKernel((void*)solve_kernel<KT>, dim3(c.grid), dim3(SOLVE_WARPS * 32), params, c.smem,
-                                        g_eigd_stream));
-  ++g_eigd_launches;
-  f->bar_base += (unsigned long long)(a.nphases - 1) * (unsigned long long)c.grid;
+  if (sub_first) {
+    subtree_kernel<KT><<<hp[0].level, SOLVE_WARPS * 32, c.smem_sub, g_eigd_stream>>>(a, 0);
+    EIGD_CUDA(cudaGetLastError());
+    ++g_eigd_launches;
+  }
+  if (a.p_end > a.p_begin) {
+    void* params[] = {(void*)&a};
+    EIGD_CUDA(cudaLaunchCooperativeKernel((void*)solve_kernel<KT>, dim3(c.grid), dim3(SOLVE_WARPS * 32), params, c.smem,
+                                          g_eigd_stream));
+    ++g_eigd_launches;
+    f->bar_base += (unsigned long long)(a.p_end - a.p_begin - 1) * (unsigned long long)c.grid;
+  }
+  if (sub_last) {
+    subtree_kernel<KT><<<hp[np - 1].level, SOLVE_WARPS * 32, c.smem_sub, g_eigd_stream>>>(a, np - 1);
+    EIGD_CUDA(cudaGetLastError());
+    ++g_eigd_launches;
+  }
   return 0;
 }
 
@@ -497,6 +979,11 @@ extern "C" int eigd_factor_solve(eigd_factor* f, const double* B, int64_t brs, i
     a.xcs = xcs;
     a.k = kc;
     a.times = g_phase_times;
+    {
+      static int dbg = -1;
+      if (dbg < 0) { const char* e = getenv("EIGD_SOLVE_DBG"); dbg = e ? atoi(e) : 0; }
+      a.dbg = dbg;
+    }
     int rc;
     SolveTiming tm;
     if (g_timing_on) {

@@ -58,7 +58,7 @@ double assign_subtrees(const eigd_symbolic* S, int cut, int nslots, std::vector<
 void build_solve_plan_host(const eigd_symbolic* S, int target_warps, int nslots, int cut_req, SolvePlanHost& P) {
   const int ns = S->nsuper;
   P.soff.assign(ns + 1, 0);
-  for (int k = 0; k < ns; ++k) P.soff[k + 1] = P.soff[k] + (int64_t)sn_fsize(S, k) * sn_ncols(S, k);
+  for (int k = 0; k < ns; ++k) P.soff[k + 1] = P.soff[k] + solve_panel_doubles(sn_fsize(S, k), sn_ncols(S, k));
 
   // ---- child slabs and overflow lists ---------------------------------------------------------
   // children 0 and 1 of a front (ascending order) write their update rows straight into the parent's
@@ -137,18 +137,23 @@ void build_solve_plan_host(const eigd_symbolic* S, int target_warps, int nslots,
     }
   }
   const int cut = P.cut_level, nl = cut + 1;
+  // front mode (default): ONE record per front in the subtree phases -- a warp brings the front's whole panel
+  // into shared memory with one bulk copy and runs all its row tiles from there; EIGD_SOLVE_FRONTS=0 keeps the
+  // one-record-per-tile form (developer comparison runs)
+  bool front_mode = true;
+  if (const char* e = getenv("EIGD_SOLVE_FRONTS")) front_mode = atoi(e) != 0;
   auto subtree_phase = [&](int dir) {
     // tiles ordered by (slot, level); table entry [slot * (nl + 1) + l] = first tile of local level l
     std::vector<std::vector<int>> bucket((size_t)nslots * nl);
     for (int k = 0; k < ns; ++k)
       if (S->sn_level[k] <= cut) bucket[(size_t)P.sub_slot[k] * nl + S->sn_level[k]].push_back(k);
-    PhaseRec ph{dir, 0, nl, nslots, (int64_t)P.sub_ptr.size(), SOLVE_TILE};
+    PhaseRec ph{dir, 0, nl, nslots, (int64_t)P.sub_ptr.size(), front_mode ? 0 : SOLVE_TILE};
     for (int s = 0; s < nslots; ++s) {
       for (int l = 0; l < nl; ++l) {
         P.sub_ptr.push_back((int)P.tiles.size());
         for (int k : bucket[(size_t)s * nl + l]) {
           int outs = dir == 0 ? sn_fsize(S, k) : sn_ncols(S, k);
-          for (int t = 0; t * SOLVE_TILE < outs; ++t) P.tiles.push_back(rec(k, t));
+          for (int t = 0; t * SOLVE_TILE < outs && (t == 0 || !front_mode); ++t) P.tiles.push_back(rec(k, t));
         }
       }
       P.sub_ptr.push_back((int)P.tiles.size());

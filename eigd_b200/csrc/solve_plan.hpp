@@ -22,6 +22,15 @@ constexpr int64_t LINK_WOFF_MASK = ((int64_t)1 << 48) - 1;
 constexpr int64_t LINK_HAS_OVF = (int64_t)1 << 56;
 constexpr int64_t LINK_HAS_CHILDREN = (int64_t)1 << 57;
 
+// doubles reserved for the f x nc solve panel of a front: an even count, so that every panel starts on a
+// 16-byte boundary and spans a multiple of 16 bytes (the unit of a bulk copy into shared memory)
+#ifdef __CUDACC__
+#define EIGD_HD __host__ __device__
+#else
+#define EIGD_HD
+#endif
+EIGD_HD inline int64_t solve_panel_doubles(int f, int nc) { return ((int64_t)f * nc + 1) & ~(int64_t)1; }
+
 // One warp tile: 32 consecutive outputs of one front.  Everything the warp needs about the front
 // travels in this one 48-byte record; the forward sweep needs no further index look-up before it
 // can read its operands (permuted right-hand side and the two child slabs are addressed by the
@@ -44,12 +53,13 @@ static_assert(sizeof(TileRec) == 48, "TileRec is read as three 16-byte words");
 struct PhaseRec {
   int dir, ws, ntiles, level;     // dir 0 forward, 1 backward
   int64_t tile_off;
-  int64_t pad;                    // tile height (= SOLVE_TILE)
+  int64_t pad;                    // level phase: tile height (= SOLVE_TILE); subtree phase: SOLVE_TILE = one record
+                                  // per 32-output tile, 0 = FRONT MODE, one record per front (tile field 0)
 };
 static_assert(sizeof(PhaseRec) == 32, "PhaseRec layout");
 
 struct SolvePlanHost {
-  std::vector<int64_t> soff;      // nsuper + 1, prefix sum of f * nc
+  std::vector<int64_t> soff;      // nsuper + 1, prefix sum of solve_panel_doubles(f, nc)
   // overflow form of the extend-add of the forward sweep (fronts with more than two children):
   // ovf_row[t] = -1, or the offset o of a list ovf[o] = count, ovf[o+1 ..] = source rows in slab 2
   std::vector<int> ovf_row;       // sum_front

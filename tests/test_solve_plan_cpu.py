@@ -90,7 +90,16 @@ def emulate(plan, S, sym_arr, dinv, b):
                 for ll in range(nl):
                     l = ll if d == 0 else nl - 1 - ll
                     for te in range(tab[l], tab[l + 1]):
-                        do_tile(int(d), tiles[te])
+                        if _to == 0:              # front mode: one record per front, the kernel runs all its tiles
+                            first, nc, nb, tile = (int(v) for v in tiles[te][:4])
+                            assert tile == 0
+                            outs = nc + nb if d == 0 else nc
+                            for t in range((outs + 31) // 32):
+                                rec = tiles[te].copy()
+                                rec[3] = t
+                                do_tile(int(d), rec)
+                        else:
+                            do_tile(int(d), tiles[te])
         else:
             for te in range(tile_off, tile_off + ntiles):
                 do_tile(int(d), tiles[te])
