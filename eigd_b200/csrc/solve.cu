@@ -28,6 +28,9 @@
 
 namespace {
 
+#ifndef EIGD_SUB_NW1
+#define EIGD_SUB_NW1 16
+#endif
 constexpr int MAX_PHASES_SMEM = 96;
 constexpr int MAX_SUB_LEVELS = 32;
 
@@ -520,11 +523,10 @@ constexpr int FRONT_DEPTH = 2;   // panel copies in flight per warp
 // and across level boundaries (panels do not depend on computed data): a FIFO of variable-size allocations in the
 // warp's ring buffer, one mbarrier per FIFO position.  The OPERANDS (right-hand side, child updates, D^-1, row
 // positions) are requested one front ahead into registers (KT <= 2).
-template <int KT>
+template <int KT, int NW, bool PIPE>
 __device__ __forceinline__ void fronts_phase(const SolveArgs& a, int dir, bool use_perm, int nl, const int* s_tab, int tb,
                                              int nrec, const int4* s_rec, int lane, int warp, double* stage, char* ring,
                                              int ring_w, unsigned long long* bars, int* s_q) {
-  constexpr bool PIPE = KT == 1;
   // the backward sweep of a multi-column solve is faster on the tile path (measured: k = 10, 95 vs 103 us at C2)
   const bool front_ok = dir == 0 || KT == 1;
   const double* panels = dir == 0 ? a.sfwd : a.sbwd;
@@ -571,7 +573,7 @@ __device__ __forceinline__ void fronts_phase(const SolveArgs& a, int dir, bool u
       if (lane == 0) { s_q[2 * e] = off; s_q[2 * e + 1] = (int)b; }
       __syncwarp();
       ++qn;
-      pte += SOLVE_WARPS;
+      pte += NW;
       p_skip();
     }
   };
@@ -581,7 +583,7 @@ __device__ __forceinline__ void fronts_phase(const SolveArgs& a, int dir, bool u
   for (int ll = 0; ll < nl; ++ll) {
     const int l = level_of(ll);
     const int t0 = s_tab[l], t1 = s_tab[l + 1];
-    for (int te = t0 + warp; te < t1; te += SOLVE_WARPS) {
+    for (int te = t0 + warp; te < t1; te += NW) {
       TileRec tr = record(te);
       const int off = s_q[2 * qh];
       const unsigned parity = (par >> qh) & 1u;
@@ -591,8 +593,8 @@ __device__ __forceinline__ void fronts_phase(const SolveArgs& a, int dir, bool u
       bool nops_ready = false;
       if constexpr (PIPE) {
         // operands of this warp's next front of the SAME level (the next level's depend on this level's results)
-        if (te + SOLVE_WARPS < t1) {
-          const TileRec nt = record(te + SOLVE_WARPS);
+        if (te + NW < t1) {
+          const TileRec nt = record(te + NW);
           if (fits(nt, (unsigned)solve_panel_doubles(nt.nc + nt.nb, nt.nc) * 8u)) {
             front_request<KT>(a, dir, use_perm, nt, lane, nops);
             nops_ready = true;
@@ -633,16 +635,16 @@ __device__ __forceinline__ void fronts_phase(const SolveArgs& a, int dir, bool u
 // A subtree phase in FRONT MODE as its own (ordinary, non-cooperative) launch: one CTA per slot.  The forward one
 // is the first thing a solve does, the backward one the last, so stream order replaces the grid barrier; the kernel
 // gets its own register / shared-memory budget (panel ring) and the level kernel keeps its L1.
-template <int KT>
-__global__ void __launch_bounds__(SOLVE_WARPS * 32, 1) subtree_kernel(SolveArgs a, int p) {
+template <int KT, int NW, bool PIPE>
+__global__ void __launch_bounds__(NW * 32, 1) subtree_kernel(SolveArgs a, int p) {
   extern __shared__ double smem[];
   __shared__ int s_tab[MAX_SUB_LEVELS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double* stage = smem + warp * (32 * KT);                 // [KT][32] per warp
-  char* ring_all = reinterpret_cast<char*>(smem + SOLVE_WARPS * 32 * KT);
-  unsigned long long* mbar_all = reinterpret_cast<unsigned long long*>(ring_all + (size_t)SOLVE_WARPS * a.ring_w);
-  int* s_q = reinterpret_cast<int*>(mbar_all + FRONT_DEPTH * SOLVE_WARPS) + 2 * FRONT_DEPTH * warp;
-  int4* s_rec = reinterpret_cast<int4*>(mbar_all + 2 * FRONT_DEPTH * SOLVE_WARPS);
+  char* ring_all = reinterpret_cast<char*>(smem + NW * 32 * KT);
+  unsigned long long* mbar_all = reinterpret_cast<unsigned long long*>(ring_all + (size_t)NW * a.ring_w);
+  int* s_q = reinterpret_cast<int*>(mbar_all + FRONT_DEPTH * NW) + 2 * FRONT_DEPTH * warp;
+  int4* s_rec = reinterpret_cast<int4*>(mbar_all + 2 * FRONT_DEPTH * NW);
   unsigned long long* bars = mbar_all + FRONT_DEPTH * warp;
   if (lane < FRONT_DEPTH) mbar_init(&bars[lane], 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -665,7 +667,7 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32, 1) subtree_kernel(SolveArgs 
       for (int e = threadIdx.x; e < 3 * nrec; e += blockDim.x) s_rec[e] = __ldg(src + e);
     }
     __syncthreads();
-    fronts_phase<KT>(a, dir, use_perm, nl, s_tab, tb, nrec, s_rec, lane, warp, stage, ring_all + (size_t)warp * a.ring_w,
+    fronts_phase<KT, NW, PIPE>(a, dir, use_perm, nl, s_tab, tb, nrec, s_rec, lane, warp, stage, ring_all + (size_t)warp * a.ring_w,
                      a.ring_w, bars, s_q);
   }
   if (use_perm) {
@@ -809,6 +811,14 @@ int upload_vec(SymDevHolder* h, const std::vector<T>& v, T** out) {
   return 0;
 }
 
+// launch shape of the subtree kernel per right-hand-side count: warps per CTA and whether the operands of the
+// next front are prefetched into registers (needs the 128-register budget of a 16-warp CTA)
+template <int KT>
+struct SubCfg {
+  static constexpr int NW = KT == 1 ? EIGD_SUB_NW1 : 16;
+  static constexpr bool PIPE = KT == 1 && NW == 16;
+};
+
 struct KernelCfg {
   bool ready = false;
   int grid = 0;
@@ -830,14 +840,17 @@ int configure(int slot) {
   int occ = 0;
   EIGD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, solve_kernel<KT>, SOLVE_WARPS * 32, c.smem));
   if (occ < 1) { eigd_set_error("solve: kernel does not fit on an SM"); return 5; }
-  // subtree kernel: staging [16][KT][32] | panel ring | 32 mbarriers | front records; 227 KB per CTA on sm_100a
+  // subtree kernel: staging [NW][KT][32] | panel ring | mbarriers + copy queue | front records; 227 KB per CTA on sm_100a
+  constexpr int NW = SubCfg<KT>::NW;
+  const size_t stage_s = (size_t)NW * 32 * KT * 8;
   const size_t budget = 227 * 1024 - 1024;
   c.rec_cap = KT <= 4 ? 512 : 256;
-  size_t ring = (budget - stage_b - 2 * FRONT_DEPTH * SOLVE_WARPS * 8 - (size_t)c.rec_cap * 48) / SOLVE_WARPS;
+  size_t ring = (budget - stage_s - 2 * FRONT_DEPTH * NW * 8 - (size_t)c.rec_cap * 48) / NW;
   ring = std::min<size_t>(ring, 10240) / 256 * 256;
   c.ring_w = (int)ring;
-  c.smem_sub = stage_b + ring * SOLVE_WARPS + 2 * FRONT_DEPTH * SOLVE_WARPS * 8 + (size_t)c.rec_cap * 48;
-  EIGD_CUDA(cudaFuncSetAttribute(subtree_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem_sub));
+  c.smem_sub = stage_s + ring * NW + 2 * FRONT_DEPTH * NW * 8 + (size_t)c.rec_cap * 48;
+  EIGD_CUDA(cudaFuncSetAttribute(subtree_kernel<KT, NW, SubCfg<KT>::PIPE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)c.smem_sub));
   c.grid = g_num_sms;
   c.ready = true;
   return 0;
@@ -860,7 +873,7 @@ int launch_solve(int slot, eigd_factor* f, SolveArgs& a) {
   a.p_end = sub_last ? np - 1 : np;
   a.bar_base = f->bar_base;
   if (sub_first) {
-    subtree_kernel<KT><<<hp[0].level, SOLVE_WARPS * 32, c.smem_sub, g_eigd_stream>>>(a, 0);
+    subtree_kernel<KT, SubCfg<KT>::NW, SubCfg<KT>::PIPE><<<hp[0].level, SubCfg<KT>::NW * 32, c.smem_sub, g_eigd_stream>>>(a, 0);
     EIGD_CUDA(cudaGetLastError());
     ++g_eigd_launches;
   }
@@ -872,7 +885,8 @@ int launch_solve(int slot, eigd_factor* f, SolveArgs& a) {
     f->bar_base += (unsigned long long)(a.p_end - a.p_begin - 1) * (unsigned long long)c.grid;
   }
   if (sub_last) {
-    subtree_kernel<KT><<<hp[np - 1].level, SOLVE_WARPS * 32, c.smem_sub, g_eigd_stream>>>(a, np - 1);
+    subtree_kernel<KT, SubCfg<KT>::NW, SubCfg<KT>::PIPE><<<hp[np - 1].level, SubCfg<KT>::NW * 32, c.smem_sub, g_eigd_stream>>>(a,
+                                                                                                                      np - 1);
     EIGD_CUDA(cudaGetLastError());
     ++g_eigd_launches;
   }

@@ -129,6 +129,36 @@ def test_factor_solve(D, nx, ny, dof, use_xy):
         assert rel(bd.cpu().numpy(), xo) < 1e-10
 
 
+@pytest.mark.parametrize("nx,ny,dof", [(250, 200, 1), (160, 120, 2)])
+def test_factor_solve_front_mode(D, nx, ny, dof):
+    """Sizes at which the solve plan has subtree phases: exercises the TMA-staged front kernels (k = 1 pipelined
+    operands, k > 1 forward fronts + backward tile path) and the persistent level kernel between them."""
+    import ctypes
+    from eigd_b200 import _lib
+    rng = np.random.default_rng(nx + ny + dof)
+    A, X = grid_matrix(nx, ny, dof, rng)
+    n = A.shape[0]
+    sym = D.Symbolic(A.indptr, A.indices, n, coords=X, dof_per_node=dof)
+    lib = _lib.load()
+    meta = np.zeros(3, dtype=np.int64)
+    lib.eigd_solve_plan_get(sym.handle, 148 * 16, 148, -2, 7, meta.ctypes.data_as(ctypes.c_void_p), 3)
+    assert meta[0] >= 0, "expected subtree phases at this size"
+    Ad = D.CsrDevice.from_scipy(A)
+    fac = D.Factor(sym, max_rhs=32).numeric(Ad.data, sym.assembly_map_device(Ad.indptr, Ad.indices))
+    for k in (1, 2, 5, 10, 16, 24):
+        B = rng.normal(size=(n, k))
+        Bd = D.to_device(B)
+        X1 = fac.solve(Bd).cpu().numpy()
+        r = np.abs(A @ X1 - B).max() / np.abs(B).max()
+        assert r < 1e-11, (k, r)
+        X2 = fac.solve(Bd).cpu().numpy()
+        assert np.array_equal(X1, X2), "solve is not bitwise reproducible"
+    b = rng.normal(size=n)
+    bd = D.to_device(b.copy())
+    fac.solve(bd, out=bd)                               # in place
+    assert np.abs(A @ bd.cpu().numpy() - b).max() / np.abs(b).max() < 1e-11
+
+
 def test_factor_indefinite(D):
     rng = np.random.default_rng(7)
     A, X = grid_matrix(50, 30, 1, rng, spd=True)

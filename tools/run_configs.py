@@ -71,6 +71,8 @@ def run_c3(args):
     out["reps"] = reps
     out["BLF"] = [float(v) for v in model.BLF]
     out["factor_info"] = model.factor.info
+    out["refine_steps"] = model.factor.refine
+    out["probe_residual_unrefined"] = model.factor._probe_residual()
     out["symbolic"] = model.symbolic[0].stats()
     res, orth = residuals(model, model.Gr, model.Kr, model.BLF, model.Qr, "buckling")
     out["eigen_residual_max"] = res
