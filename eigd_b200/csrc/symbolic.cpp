@@ -9,6 +9,7 @@
 #include "../../include/eigd_b200.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -485,7 +486,8 @@ extern "C" int eigd_symbolic_create(int n, const int* indptr, const int* indices
     if (opts[2] > 0) S->nd_leaf = opts[2];
     if (opts[3] >= 0) S->relax = opts[3];
   }
-  if (S->max_super_cols > 256) S->max_super_cols = 256;  // solve kernels stage w1 in shared memory
+  if (const char* e = getenv("EIGD_MAX_SUPER_COLS")) S->max_super_cols = atoi(e);   // developer override (tuning runs)
+  if (S->max_super_cols > 512) S->max_super_cols = 512;  // widest pivot block the factor kernels handle (factor.cu)
   if (S->leaf_cols > S->max_super_cols) S->leaf_cols = S->max_super_cols;
 
   // ---- ordering ---------------------------------------------------------------------
