@@ -1,0 +1,38 @@
+"""Developer profile of the numpy-API (end-to-end) gradient step of bench.py: cProfile of the host side."""
+import cProfile, pstats, sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import eigd_b200 as E
+from eigd_b200 import device as D, topo as T
+D.init()
+N, SIGMA = 10, -0.1
+model = T.make_thermal_model(nx=500, ny=500, N=N, m=60, sigma=SIGMA, solver_type="IRAM", adjoint_method="sibk",
+                             adjoint_options={"lanczos_guess": True}, rtol=1e-10, deriv_type="tensor", seed=0)
+x_d = D.to_device(np.random.default_rng(0).uniform(0.3, 1.0, model.nnodes))
+vec_h = np.random.default_rng(12345).uniform(size=model.nnodes)
+model.initialize(x=x_d)
+K_h, M_h = model.K.to_scipy(), model.M.to_scipy()
+mat_h = (K_h - SIGMA * M_h).tocsc()
+prob = model.prob
+
+def step():
+    f = E.SpLuOperator(mat_h, coords=model.X, dof_per_node=1)
+    s = E.IRAM(N=N, m=60); s.seed = 0
+    lam, Phi = s.solve(K_h, M_h, f, SIGMA)
+    c = Phi.T @ vec_h
+    Phib = 2.0 * np.outer(vec_h, c / lam); lamb = -(c * c) / lam**2
+    Phib[:, 0], lamb[0] = 0.0, 0.0
+    psi, data = s.solve_adjoint(Phib, method="sibk", rtol=1e-10, lanczos_guess=True)
+    dfdx = np.zeros(prob.nelems)
+    s.add_total_derivative(lamb, Phib, psi, prob.dAdx, prob.dBdx, dfdx, adj_corr_data=data, deriv_type="tensor")
+    torch.cuda.synchronize()
+    return dfdx
+
+for _ in range(3): step()
+t0 = time.perf_counter()
+for _ in range(3): step()
+print("e2e step %.1f ms" % ((time.perf_counter() - t0) / 3 * 1e3))
+pr = cProfile.Profile(); pr.enable()
+for _ in range(3): step()
+pr.disable()
+pstats.Stats(pr).sort_stats("tottime").print_stats(22)
