@@ -301,6 +301,7 @@ struct FrontRing {
   unsigned uses[2];            // completed copies per barrier (parity of the next wait)
 };
 
+constexpr int FRONT_TILES_MAX = 8;   // row tiles / row chunks of a front in front mode (non-pipelined form): f <= 256
 constexpr int FRONT_RT = 3;    // row tiles (forward) / row chunks (backward) a pipelined front may have: f <= 96
 
 // Operands of one front, REQUESTED one front ahead (software pipeline in registers, KT <= 2): by the time the
@@ -411,7 +412,7 @@ __device__ __forceinline__ void front_compute(const SolveArgs& a, int dir, bool 
       __syncwarp();
       if (!(a.dbg & 2)) mbar_wait(bar, parity);
 #pragma unroll
-      for (int t = 0; t < (PIPE ? FRONT_RT : 8); ++t) {
+      for (int t = 0; t < (PIPE ? FRONT_RT : FRONT_TILES_MAX); ++t) {
         if (t >= ntile) break;
         const int row = t * SOLVE_TILE + lane;
         double acc[KT];
@@ -472,7 +473,7 @@ __device__ __forceinline__ void front_compute(const SolveArgs& a, int dir, bool 
       for (int r = 0; r < KT; ++r) acc[r] = 0.0;
       const double* colp = buf + min(lane, nc - 1);
 #pragma unroll
-      for (int t = 0; t < (PIPE ? FRONT_RT : 8); ++t) {
+      for (int t = 0; t < (PIPE ? FRONT_RT : FRONT_TILES_MAX); ++t) {
         const int cc = t * SOLVE_TILE;
         if (cc >= f) break;
         const int nrow = min(32, f - cc);
@@ -535,7 +536,7 @@ __device__ __forceinline__ void fronts_phase(const SolveArgs& a, int dir, bool u
     return q < nrec ? unpack_tile(s_rec[3 * q], s_rec[3 * q + 1], s_rec[3 * q + 2]) : load_tile(a.tiles + te);
   };
   auto fits = [&](const TileRec& t, unsigned b) {
-    return front_ok && t.nc <= 32 && (int)b <= ring_w && (!PIPE || t.nc + t.nb <= FRONT_RT * SOLVE_TILE);
+    return front_ok && t.nc <= 32 && (int)b <= ring_w && t.nc + t.nb <= (PIPE ? FRONT_RT : FRONT_TILES_MAX) * SOLVE_TILE;
   };
   auto level_of = [&](int ll) { return dir == 0 ? ll : nl - 1 - ll; };
   // producer cursor (pl, pte): next front whose panel copy has not been requested yet
