@@ -233,6 +233,73 @@ basis_axpy_kernel(int64_t n, int j, const double* __restrict__ V, int64_t ldv, c
   }
 }
 
+// Same product for the reference's row-major (n, k) operands (unit column stride): no shared-memory staging and
+// no block barrier in the row loop -- every CTA owns one contiguous range of rows, a thread (row group g, 4x4
+// output tile p) reads its 4 + 4 operand entries of UNR rows straight from global memory (the rows of a warp's
+// threads are adjacent, the re-reads by the other tiles of the same row hit L1) before it does the FMAs.
+// The staged kernel above spent its time in load -> barrier -> compute -> barrier per 64 rows (63 us for
+// 2 x 20 MB at n = 251k); this one is bound by the loads.
+__global__ void __launch_bounds__(TN_THREADS)
+gemm_tn_rowmajor_partial(int64_t n, int k1, int k2, const double* __restrict__ X, int64_t xrs,
+                         const double* __restrict__ Y, int64_t yrs, double* __restrict__ partial) {
+  extern __shared__ double sm[];
+  constexpr int UNR = 4;
+  const int nta = (k1 + 3) >> 2, ntb = (k2 + 3) >> 2;
+  const int npairs = nta * ntb;
+  const int G = TN_THREADS / npairs;
+  const int g = threadIdx.x / npairs, p = threadIdx.x - g * npairs;
+  const int a0 = (p / ntb) * 4, b0 = (p % ntb) * 4;
+  const bool active = g < G;
+  double acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+  const int64_t per = (n + gridDim.x - 1) / gridDim.x;
+  const int64_t r0 = (int64_t)blockIdx.x * per, r1 = min(n, r0 + per);
+  if (active) {
+    for (int64_t rb = r0 + g; rb < r1; rb += (int64_t)G * UNR) {
+      double xa[UNR][4], yb[UNR][4];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int64_t r = rb + (int64_t)u * G;
+        const bool ok = r < r1;
+        const double* xp = X + r * xrs + a0;
+        const double* yp = Y + r * yrs + b0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) xa[u][i] = (ok && a0 + i < k1) ? __ldg(xp + i) : 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) yb[u][j] = (ok && b0 + j < k2) ? __ldg(yp + j) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fma(xa[u][i], yb[u][j], acc[i][j]);
+    }
+  }
+  // reduce over the row groups in a fixed order: group 0 owns the result
+  double* red = sm;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) red[(i * 4 + j) * TN_THREADS + threadIdx.x] = active ? acc[i][j] : 0.0;
+  __syncthreads();
+  if (g == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (a0 + i < k1 && b0 + j < k2) {
+          double s = 0.0;
+          for (int gg = 0; gg < G; ++gg) s += red[(i * 4 + j) * TN_THREADS + gg * npairs + p];
+          partial[(int64_t)blockIdx.x * (k1 * k2) + (a0 + i) * k2 + (b0 + j)] = s;
+        }
+      }
+  }
+}
+
 constexpr int NN_R = 32;
 constexpr int NN_K1MAX = 64;
 constexpr int NN_K2MAX = 32;
@@ -262,6 +329,27 @@ gemm_nn_kernel(int64_t n, int k1, int k2, double alpha, const double* __restrict
       double y0 = (beta == 0.0) ? 0.0 : beta * Y[yi];
       Y[yi] = fma(alpha, s, y0);
     }
+  }
+}
+
+// Same update for row-major X (n, k1) and Y (n, k2): one output entry per thread (coalesced Y), the k1 entries of
+// its X row come through L1 (the k2 threads of a row share them), S sits in shared memory; no barrier per tile.
+__global__ void __launch_bounds__(256)
+gemm_nn_rowmajor_kernel(int64_t n, int k1, int k2, double alpha, const double* __restrict__ X, int64_t xrs,
+                        const double* __restrict__ S, int lds, double beta, double* __restrict__ Y, int64_t yrs) {
+  __shared__ double Ss[NN_K1MAX * NN_K2MAX];
+  for (int e = threadIdx.x; e < k1 * k2; e += blockDim.x) Ss[e] = S[(e / k2) * lds + (e % k2)];
+  __syncthreads();
+  const int64_t total = n * k2;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = e / k2;
+    const int b = (int)(e - i * k2);
+    const double* xp = X + i * xrs;
+    const int64_t yi = i * yrs + b;
+    const double y0 = (beta == 0.0) ? 0.0 : beta * Y[yi];
+    double s = 0.0;
+    for (int a = 0; a < k1; ++a) s = fma(__ldg(xp + a), Ss[a * k2 + b], s);
+    Y[yi] = fma(alpha, s, y0);
   }
 }
 
@@ -386,8 +474,12 @@ extern "C" int eigd_gemm_tn(int64_t n, int k1, int k2, const double* X, int64_t 
       size_t tile_bytes = (size_t)TN_R * (ka + 1 + kb + 1) * sizeof(double);
       size_t red_bytes = (size_t)16 * TN_THREADS * sizeof(double);
       size_t smem = tile_bytes > red_bytes ? tile_bytes : red_bytes;
-      EIGD_LAUNCH(gemm_tn_partial, grid, TN_THREADS, smem, n, ka, kb, X + (int64_t)a0 * xcs, xrs, xcs,
-                  Y + (int64_t)b0 * ycs, yrs, ycs, work);
+      if (xcs == 1 && ycs == 1) {
+        EIGD_LAUNCH(gemm_tn_rowmajor_partial, grid, TN_THREADS, red_bytes, n, ka, kb, X + a0, xrs, Y + b0, yrs, work);
+      } else {
+        EIGD_LAUNCH(gemm_tn_partial, grid, TN_THREADS, smem, n, ka, kb, X + (int64_t)a0 * xcs, xrs, xcs,
+                    Y + (int64_t)b0 * ycs, yrs, ycs, work);
+      }
       EIGD_CHECK_LAUNCH();
       EIGD_LAUNCH(reduce_partials, (ka * kb + 7) / 8, 256, 0, grid, ka, kb, work, C + (int64_t)a0 * ldc + b0, ldc);
       EIGD_CHECK_LAUNCH();
@@ -409,8 +501,15 @@ extern "C" int eigd_gemm_nn(int64_t n, int k1, int k2, double alpha, const doubl
     int kb = min(NN_K2MAX, k2 - b0);
     for (int a0 = 0; a0 < k1; a0 += NN_K1MAX) {
       int ka = min(NN_K1MAX, k1 - a0);
-      EIGD_LAUNCH(gemm_nn_kernel, grid, 256, 0, n, ka, kb, alpha, X + (int64_t)a0 * xcs, xrs, xcs,
-                  S + (int64_t)a0 * lds + b0, lds, (a0 == 0 ? beta : 1.0), Y + (int64_t)b0 * ycs, yrs, ycs);
+      if (xcs == 1 && ycs == 1) {
+        int64_t ge = (n * kb + 255) / 256;
+        int g2 = (int)(ge < 148 * 16 ? ge : 148 * 16);
+        EIGD_LAUNCH(gemm_nn_rowmajor_kernel, g2, 256, 0, n, ka, kb, alpha, X + a0, xrs, S + (int64_t)a0 * lds + b0, lds,
+                    (a0 == 0 ? beta : 1.0), Y + b0, yrs);
+      } else {
+        EIGD_LAUNCH(gemm_nn_kernel, grid, 256, 0, n, ka, kb, alpha, X + (int64_t)a0 * xcs, xrs, xcs,
+                    S + (int64_t)a0 * lds + b0, lds, (a0 == 0 ? beta : 1.0), Y + (int64_t)b0 * ycs, yrs, ycs);
+      }
       EIGD_CHECK_LAUNCH();
     }
   }
