@@ -111,3 +111,26 @@ def test_nf_iram_gradient():
     assert rel(Pa, g["Phi_all"][:, 3:]) < 1e-6
     R0, R1 = Phi[:, :3], g["Phi_all"][:, :3]
     assert np.abs(R0 @ (R0.T @ (B @ R1)) - R1).max() < 1e-6 * np.abs(R1).max()
+
+
+def test_buckling_fe_oracle_matches_reference_example():
+    """oracle/buckling_oracle.py against the frozen outputs of examples/buckling.py: reduced K, fundamental path,
+    reduced G(u, x), and the three sensitivity callbacks on seeded operands."""
+    import buckling_oracle as bo
+    g = load_golden("buckling_basiclanczos")
+    E, nu, p, rho0_K, rho0_G = (float(v) for v in g["material"])
+    o = bo.BucklingOracle(g["conn"], g["X"], g["reduced"], g["f"], E=E, nu=nu, p=p, rho0_K=rho0_K, rho0_G=rho0_G)
+    rhoE = g["rhoE"]
+    u, Kr, _ = o.fundamental_path(rhoE)
+    Kr.sort_indices()
+    assert np.array_equal(Kr.indptr, g["B_indptr"]) and np.array_equal(Kr.indices, g["B_indices"])
+    assert rel(Kr.data, g["B_data"]) < 1e-13
+    assert rel(u, g["u"]) < 1e-11
+    Gr = o.reduce_matrix(o.stress_stiffness(rhoE, g["u"]))
+    Gr.sort_indices()
+    assert np.array_equal(Gr.indices, g["A_indices"])
+    assert rel(Gr.data, g["A_data"]) < 1e-13
+    W, V = o.full_vector(g["cb_W"]), o.full_vector(g["cb_V"])
+    assert rel(o.dG_du(rhoE, W, V), g["cb_dGdu"]) < 1e-12
+    assert rel(o.scatter(o.dG_dx(rhoE, g["u"], W, V)), g["cb_dGdx"]) < 1e-12
+    assert rel(o.scatter(o.dK(rhoE, W, V)), g["cb_dKdx"]) < 1e-12
