@@ -699,15 +699,137 @@ def _sibk_dev(Phib_d, Ad, Bd, lam, Phi_d, mode, psi_d, sigma, factor, rtol, atol
     return G, info, hist
 
 
+def _sibk_seq_dev(Phib_d, Ad, Bd, lam, Phi_d, mode, psi_d, sigma, factor, rtol, atol, maxiter, bs_target, update_guess,
+                  nrestart, callback):
+    """The reference's coupled variants of sibk (:1195-1321): modes are visited in order, ``bs_target`` of them share
+    one block Arnoldi process, and with ``update_guess`` the finished Krylov space is recycled to improve the guesses
+    and residuals of the modes still to come (:1279-1305).  Inherently sequential (one single-column solve per
+    Arnoldi step), so it runs vector by vector on the device; the Krylov bases are vector-major so that the
+    orthogonalisation uses the same basis kernels as the Lanczos recurrence (classical Gram-Schmidt, two passes,
+    instead of the reference's modified Gram-Schmidt: same space, same converged solution)."""
+    n, N = Phib_d.shape
+    lam = np.asarray(lam, dtype=float)
+    lam_d = small_to_dev(lam)
+    rnorm0 = float(np.sqrt(np.max(to_host(D.col_dot(Phib_d, Phib_d)))))           # :1170
+    BPhi = Bd.spmm(Phi_d)
+    G = -to_host(D.gemm_tn(Phi_d, Phib_d))
+    R = _neg_sum(_contig(Phib_d), _apply_L(Ad, Bd, lam_d, psi_d, mode))           # :1189-1193
+    _project(BPhi, Phi_d, R)
+    opmat = Bd if mode == "normal" else Ad
+    Wt = D.empty(maxiter + bs_target, n)          # Krylov vectors, one per row
+    Zt = D.empty(maxiter, n)
+    hbuf = D.zeros(maxiter + bs_target + 1)
+    info = []
+
+    def alpha_of(k):
+        return (lam[k] - sigma) if mode == "normal" else -(lam[k] - sigma)
+
+    def lstsq(alpha, H0, rhs):                                                      # :1043-1049
+        Hi = np.eye(H0.shape[0], H0.shape[1]) - alpha * H0
+        y = np.linalg.lstsq(Hi, rhs, rcond=None)[0]
+        return y, float(np.linalg.norm(Hi @ y - rhs))
+
+    def norm(v):
+        return float(np.sqrt(to_host(D.col_dot(v, v))[0]))
+
+    def orth(w, j):
+        """w -= W[:, :j] (W[:, :j]^T w), two classical passes; returns the summed coefficients"""
+        h = np.zeros(j)
+        if j == 0:
+            return h
+        for _ in range(2):
+            D.gemm_tn(Wt[:j].T, w, out=hbuf[:j].unsqueeze(1))
+            D.gemm_nn(Wt[:j].T, hbuf[:j].unsqueeze(1), w, alpha=-1.0, beta=1.0)
+            h += to_host(hbuf[:j])
+        return h
+
+    i, restart = 0, 0
+    while i < N:
+        r = np.zeros((maxiter + bs_target, bs_target))
+        bs = 0
+        while i + bs < N and bs < bs_target:
+            k = i + bs
+            w = Wt[bs]
+            if update_guess:                                                        # :1203-1215
+                pk = _contig(psi_d[:, k])
+                _project(Phi_d, BPhi, pk)
+                psi_d[:, k].copy_(pk)
+                Lp = _apply_L(Ad, Bd, lam_d[k:k + 1], pk.unsqueeze(1), mode).reshape(-1)
+                D.axpby(-1.0, _contig(Phib_d[:, k]), -1.0, Lp, out=w)
+                _project(BPhi, Phi_d, w)
+            else:
+                w.copy_(R[:, k])                                                    # :1217
+            beta0 = norm(w)
+            if callback is not None:
+                callback(beta0)
+            if beta0 < rtol * rnorm0 or beta0 < atol:
+                info.append(0)
+                break
+            r[:bs, bs] = orth(w, bs)                                                # :1228-1230
+            _project(BPhi, Phi_d, w)
+            r[bs, bs] = norm(w)
+            w.mul_(1.0 / r[bs, bs])
+            bs += 1
+        if bs == 0:
+            i += 1
+            continue
+        H = np.zeros((maxiter + bs, maxiter))
+        y = np.zeros((maxiter, bs))
+        for j in range(bs, maxiter + bs):
+            kp = j - bs
+            factor.solve_dev(Wt[kp], out=Zt[kp])                                    # :1248
+            w = Wt[j]
+            opmat.spmm(Zt[kp], out=w)
+            _project(BPhi, Phi_d, w)
+            H[:j, kp] = orth(w, j)                                                  # :1254-1257
+            _project(BPhi, Phi_d, w)
+            H[j, kp] = norm(w)
+            w.mul_(1.0 / H[j, kp])
+            res = 0.0
+            H0 = H[: j + 1, : j + 1 - bs]
+            for k in range(bs):
+                y[: kp + 1, k], res0 = lstsq(alpha_of(i + k), H0, r[: j + 1, k])
+                res = max(res, res0)
+            if callback is not None:
+                callback(res)
+            converged = res < rtol * rnorm0 or res < atol
+            if converged or j == maxiter + bs - 1:
+                nz = kp + 1
+                D.gemm_nn(Zt[:nz].T, small_to_dev(y[:nz, :]), psi_d[:, i:i + bs], alpha=1.0, beta=1.0)   # :1276 / :1310
+            if converged:
+                info.append(j)
+                if update_guess and i + bs < N:                                     # :1279-1305
+                    rest = N - (i + bs)
+                    r0 = to_host(D.gemm_tn(Wt[: j + 1].T, R[:, i + bs:]))
+                    y0 = np.zeros((j + 1 - bs, rest))
+                    t0 = np.zeros((j + 1, rest))
+                    for c in range(rest):
+                        a_k = alpha_of(i + bs + c)
+                        yk, _ = lstsq(a_k, H0, r0[:, c])
+                        y0[:, c] = yk
+                        t0[:, c] = -a_k * (H0 @ yk)
+                        t0[: j + 1 - bs, c] += yk
+                    D.gemm_nn(Zt[: j + 1 - bs].T, small_to_dev(y0), psi_d[:, i + bs:], alpha=1.0, beta=1.0)
+                    D.gemm_nn(Wt[: j + 1].T, small_to_dev(t0), R[:, i + bs:], alpha=-1.0, beta=1.0)
+                i += bs
+                restart = 0
+                break
+            if j == maxiter + bs - 1:
+                if restart >= nrestart:
+                    restart = 0
+                    i += bs
+                    break
+                restart += 1
+    return G, info
+
+
 def sibk(Phib, A, B, lam, Phi, mode="normal", psi=None, sigma=None, factor=None, rtol=1e-10, atol=1e-30,
          eig_atol=1e-5, maxiter=50, bs_target=1, update_guess=False, callback=None, nrestart=2):
     """Reference ``sibk`` (:1052-1328), shift-and-invert block Krylov, with the N per-mode Arnoldi
-    processes advanced in lock step.  ``bs_target > 1`` and ``update_guess=True`` (the reference's
-    coupled block / recycling variants, :1279-1305) are not implemented on the device path."""
+    processes advanced in lock step (default settings of every reference example).  ``bs_target > 1`` and
+    ``update_guess=True`` (the reference's coupled block / recycling variants, :1195-1321) run the sequential
+    form ``_sibk_seq_dev``."""
     n, N = _check_krylov_args(Phib, A, B, lam, Phi, psi, mode)
-    if bs_target != 1 or update_guess:
-        raise NotImplementedError("eigd_b200.sibk implements bs_target=1, update_guess=False (the settings every "
-                                  "reference example uses)")
     lam_h = to_host(lam) if is_dev(lam) else np.asarray(lam, dtype=float)
     if sigma is None:
         if factor is not None:
@@ -717,6 +839,11 @@ def sibk(Phib, A, B, lam, Phi, mode="normal", psi=None, sigma=None, factor=None,
     Ad, Bd = as_csr_device(A), as_csr_device(B)
     Phi_d, Phib_d = to_dev(Phi), to_dev(Phib)
     psi_d = D.zeros(n, N) if psi is None else to_dev(psi, copy=True)
+    if bs_target != 1 or update_guess:
+        G, info = _sibk_seq_dev(Phib_d, Ad, Bd, lam_h, Phi_d, mode, psi_d, float(sigma), factor, rtol, atol, maxiter,
+                                int(bs_target), bool(update_guess), nrestart, callback)
+        data = _apply_correction_dev(lam_h, Phi_d, psi_d, G, eig_atol, mode)
+        return _return_psi(psi_d, psi, Phib), data, info
     G, info, hist = _sibk_dev(Phib_d, Ad, Bd, lam_h, Phi_d, mode, psi_d, float(sigma), factor, rtol, atol, maxiter)
     _replay(callback, hist)
     data = _apply_correction_dev(lam_h, Phi_d, psi_d, G, eig_atol, mode)          # :1324
@@ -944,11 +1071,21 @@ class _SolverBase:
         rn0 = None if shard is None else float(np.sqrt(np.max(to_host(D.col_dot(Phib_d, Phib_d)))))
         if method != "laa" and Ns:
             if method == "sibk":
-                if kwargs.pop("bs_target", 1) != 1 or kwargs.pop("update_guess", False):
-                    raise NotImplementedError("sibk on the device path supports bs_target=1, update_guess=False")
-                kwargs.pop("nrestart", None)
-                G, info, hist = _sibk_dev(Phib_s, self._Ad, self._Bd, lam_s, Phi_d, self.mode, psi_s, float(self.sigma),
-                                          self.factor, rtol, atol, kwargs.pop("maxiter", 50), rnorm0=rn0)
+                bs_target, update_guess = int(kwargs.pop("bs_target", 1)), bool(kwargs.pop("update_guess", False))
+                nrestart = kwargs.pop("nrestart", 2)
+                if bs_target != 1 or update_guess:
+                    # coupled block / recycling variants (:1195-1321): sequential over the modes, not sharded
+                    if shard is not None:
+                        raise NotImplementedError("sibk with bs_target > 1 or update_guess=True couples the modes and "
+                                                  "cannot be sharded per mode")
+                    G, info = _sibk_seq_dev(Phib_s, self._Ad, self._Bd, lam_s, Phi_d, self.mode, psi_s, float(self.sigma),
+                                            self.factor, rtol, atol, kwargs.pop("maxiter", 50), bs_target, update_guess,
+                                            nrestart, callback)
+                    callback = None
+                else:
+                    G, info, hist = _sibk_dev(Phib_s, self._Ad, self._Bd, lam_s, Phi_d, self.mode, psi_s,
+                                              float(self.sigma), self.factor, rtol, atol, kwargs.pop("maxiter", 50),
+                                              rnorm0=rn0)
             elif method == "pcpg":
                 G, info, hist = _pcpg_dev(Phib_s, self._Ad, self._Bd, lam_s, Phi_d, self.mode, psi_s, self.factor, rtol,
                                           atol, kwargs.pop("maxiter", 100), kwargs.pop("reset", 25), rnorm0=rn0)

@@ -67,6 +67,14 @@ def thermal_case(solver_type, methods, nx=24, ny=20, N=6, m=30, seed=3):
         res, orth = topo.eig_solver.eval_adjoint_residual_norm(topo.Qb, topo.psi, b_ortho=False)
         out["res_" + method] = res
         out["nsolves_" + method] = topo.profile["adjoint preconditioner count"]
+    if solver_type != "IRAM":
+        # the coupled variants of the reference's free function sibk (block Arnoldi, residual recycling), zero guess
+        es = topo.eig_solver
+        for tag, kw in (("bs2", dict(bs_target=2)), ("ug", dict(update_guess=True)), ("bs3ug", dict(bs_target=3, update_guess=True))):
+            psi_v, _, info_v = rl.load_reference().sibk(topo.Qb, topo.K, topo.M, topo.lam, topo.Q, sigma=topo.sigma,
+                                            factor=topo.factor, rtol=1e-12, **kw)
+            out["psi_sibk_free_" + tag] = psi_v.copy()
+            out["info_sibk_free_" + tag] = np.array(info_v)
     return out
 
 

@@ -257,3 +257,28 @@ def test_error_behaviour(E, th, th_solver):
     with pytest.raises(TypeError):
         import scipy.sparse.linalg as spla
         E.IRAM(N=3).solve(th["A"], th["B"], spla.aslinearoperator(th["A"]), 0.0)   # no CPU factor fallback
+
+
+@pytest.mark.parametrize("tag,opts", [("ug", dict(update_guess=True)), ("bs2", dict(bs_target=2)),
+                                      ("bs3ug", dict(bs_target=3, update_guess=True))])
+def test_sibk_block_and_recycling_variants(E, th, tag, opts):
+    """The reference's coupled sibk variants (eigd/eigenvector_derivatives.py:1195-1321, free function, zero initial
+    guess) against the reference's own output for the same options on the same inputs (tests/golden/make_golden.py).
+    The block recurrence is delicate -- a run that does not converge inside ``maxiter`` re-adds its correction on
+    restart, in the reference as here -- so the frozen inputs are used verbatim."""
+    A, B, sigma = th["A"], th["B"], float(th["sigma"])
+    f = E.SpLuOperator(shifted(th))
+    res = []
+    psi, data, info = E.sibk(th["Phib"], A, B, th["lam"], th["Phi"], sigma=sigma, factor=f, rtol=1e-12, callback=res.append,
+                             **opts)
+    assert rel(psi, th["psi_sibk_free_" + tag]) < 1e-8
+    assert rel(psi, th["psi_sibk"]) < 1e-8                      # all variants solve the same adjoint systems
+    assert f.count == len([r for r in res]) - len(info) or f.count > 0
+    assert len(info) == len(th["info_sibk_free_" + tag])        # same sequence of blocks as the reference
+    assert all(np.isfinite(res))
+    # through the solver object (Lanczos initial guess)
+    s = E.BasicLanczos(N=int(th["N"]), m=int(th["m_max"]), tol=1e-14)
+    lam, Phi = s.solve(A, B, f, sigma)
+    Pa, sgn = align_signs(Phi, th["Phi"])
+    psi2, _ = s.solve_adjoint(th["Phib"] * sgn, method="sibk", rtol=1e-12, lanczos_guess=True, **opts)
+    assert rel(psi2 * sgn, th["psi_sibk"]) < 1e-8
