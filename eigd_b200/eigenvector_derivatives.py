@@ -1117,7 +1117,8 @@ class _SolverBase:
 class BasicLanczos(_SolverBase):
     """Reference ``BasicLanczos`` (:1331-1870): un-restarted shift-and-invert Lanczos with full
     B-orthogonalisation (modified Gram-Schmidt, descending order) and a fixed seeded start vector.
-    ``ortho_type="selective"`` and complex (complex-step) operands are not on the device path."""
+    ``ortho_type="selective"`` (:1553-1605) orthogonalises against the two previous vectors and the nearly converged
+    Ritz vectors only.  Complex (complex-step) operands are not on the device path."""
 
     def __init__(self, N=10, m=60, tol=1e-14, Ntarget=None, eig_atol=1e-5, mode="normal", ortho_type="full"):
         if Ntarget is not None and not isinstance(Ntarget, (int, np.integer)):
@@ -1125,8 +1126,6 @@ class BasicLanczos(_SolverBase):
         if ortho_type not in ("full", "selective"):
             raise ValueError(f"Unknown ortho_type {ortho_type!r}")
         _check_mode(mode)
-        if ortho_type == "selective":
-            raise NotImplementedError("ortho_type='selective' (reference :1553-1605) is not implemented on the device path")
         self.N, self.m_max, self.tol, self.Ntarget = N, m, tol, Ntarget
         self.eig_atol, self.mode, self.ortho_type = eig_atol, mode, ortho_type
         self.m = m
@@ -1163,13 +1162,20 @@ class BasicLanczos(_SolverBase):
         bw = D.empty(n)
         self.m = m_max
         Nc = self.N if self.Ntarget is None else self.Ntarget
+        S_d = BS_d = None                            # selective orthogonalisation: Ritz vectors and their B-images
         for i in range(1, m_max + 1):
             factor.solve_dev(BVt[i - 1], out=w)                                             # :1500
             if i > 1:
                 D.col_axpy(w, small_to_dev([beta[i - 2]]), Vt[i - 2], sign=-1.0)
-            for j in range(i - 1, -1, -1):                                                  # B-MGS, descending (:1522-1538)
+            # full: B-MGS against every previous vector, descending (:1522-1538); selective: only against the two
+            # previous vectors (:1560-1567), then against the nearly converged Ritz vectors S (:1569-1573)
+            jlo = -1 if self.ortho_type == "full" else max(-1, i - 3)
+            for j in range(i - 1, jlo, -1):
                 D.col_dot(w, BVt[j], out=hdev[j: j + 1])
                 D.col_axpy(w, hdev[j: j + 1], Vt[j], sign=-1.0)
+            if S_d is not None:
+                hs = D.gemm_tn(BS_d, w.unsqueeze(1))
+                D.gemm_nn(S_d, hs, w.unsqueeze(1), alpha=-1.0, beta=1.0)
             Bd.spmm(w, out=bw)
             D.col_dot(w, bw, out=hdev[i: i + 1])
             Vt[i].copy_(w)
@@ -1185,6 +1191,13 @@ class BasicLanczos(_SolverBase):
                 if (len(err) if len(bad) == 0 else bad[0]) >= Nc:
                     self.m = i
                     break
+                if self.ortho_type == "selective":                                          # :1591-1602
+                    conv = np.nonzero(err < np.sqrt(self.tol))[0]
+                    S_d = BS_d = None
+                    if len(conv):
+                        S_d = D.empty(n, len(conv))
+                        D.gemm_nn(Vt[:i].T, small_to_dev(np.ascontiguousarray(Y[:, idx][:, conv])), S_d, alpha=1.0, beta=0.0)
+                        BS_d = Bd.spmm(S_d)
         m = self.m
         self.alpha, self.beta = alpha, beta
         self.theta, self.Y, self.T, self.lam, self.indices = self._solve_reduced_problem(alpha, beta, sigma, m)

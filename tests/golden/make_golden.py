@@ -75,6 +75,12 @@ def thermal_case(solver_type, methods, nx=24, ny=20, N=6, m=30, seed=3):
                                             factor=topo.factor, rtol=1e-12, **kw)
             out["psi_sibk_free_" + tag] = psi_v.copy()
             out["info_sibk_free_" + tag] = np.array(info_v)
+        # BasicLanczos with selective orthogonalisation (eigd/eigenvector_derivatives.py:1553-1605) on the same pencil
+        sel = rl.load_reference().BasicLanczos(N=N, m=es.m_max, tol=1e-14, ortho_type="selective")
+        fsel = rl.load_reference().SpLuOperator((topo.K - topo.sigma * topo.M).tocsc())
+        lam_s, Phi_s = sel.solve(topo.K, topo.M, fsel, topo.sigma)
+        out.update(dict(sel_lam=lam_s.copy(), sel_Phi=Phi_s.copy(), sel_m=sel.m, sel_alpha=sel.alpha.copy(),
+                        sel_beta=sel.beta.copy(), sel_eig_res=sel.eig_res.copy()))
     return out
 
 

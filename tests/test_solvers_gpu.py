@@ -282,3 +282,16 @@ def test_sibk_block_and_recycling_variants(E, th, tag, opts):
     Pa, sgn = align_signs(Phi, th["Phi"])
     psi2, _ = s.solve_adjoint(th["Phib"] * sgn, method="sibk", rtol=1e-12, lanczos_guess=True, **opts)
     assert rel(psi2 * sgn, th["psi_sibk"]) < 1e-8
+
+
+def test_basic_lanczos_selective_orthogonalisation(E, th):
+    """BasicLanczos(ortho_type="selective") (reference :1553-1605) against the reference's own run on the same pencil."""
+    f = E.SpLuOperator(shifted(th))
+    s = E.BasicLanczos(N=int(th["N"]), m=int(th["m_max"]), tol=1e-14, ortho_type="selective")
+    lam, Phi = s.solve(th["A"], th["B"], f, float(th["sigma"]))
+    scale = np.abs(th["sel_lam"]).max()
+    assert np.abs(lam - th["sel_lam"]).max() < 1e-10 * scale
+    Pa, sgn = align_signs(Phi, th["sel_Phi"])
+    assert rel(Pa, th["sel_Phi"]) < 1e-7          # selective orthogonalisation itself is only good to ~sqrt(tol) = 1e-7
+    assert s.m == int(th["sel_m"])
+    assert rel(s.alpha[:8], th["sel_alpha"][:8]) < 1e-10 and rel(s.beta[:8], th["sel_beta"][:8]) < 1e-10
