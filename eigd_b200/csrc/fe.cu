@@ -258,6 +258,32 @@ extern "C" int eigd_node_gather(int nnodes, const int* d_nptr, const int* d_nele
   return 0;
 }
 
+// ---- smooth Heaviside projection of the filtered density (examples/node_filter.py:174-181, 193-203) ------------
+// forward : out = (tanh(beta eta) + tanh(beta (rho - eta))) / (tanh(beta eta) + tanh(beta (1 - eta)))
+// gradient: out = g * (beta / denom) / cosh(beta (rho - eta))^2          (rho = the filtered, unprojected field)
+namespace {
+__global__ void filter_project_kernel(int n, double beta, double eta, const double* __restrict__ rho,
+                                      const double* __restrict__ g, double* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double denom = tanh(beta * eta) + tanh(beta * (1.0 - eta));
+  const double t = beta * (rho[i] - eta);
+  if (g) {
+    const double c = cosh(t);
+    out[i] = g[i] * (beta / denom) / (c * c);
+  } else {
+    out[i] = (tanh(beta * eta) + tanh(t)) / denom;
+  }
+}
+}  // namespace
+
+extern "C" int eigd_filter_project(int n, double beta, double eta, const double* d_rho, const double* d_g, double* d_out) {
+  if (n <= 0) return 0;
+  EIGD_LAUNCH(filter_project_kernel, (n + 255) / 256, 256, 0, n, beta, eta, d_rho, d_g, d_out);
+  EIGD_CHECK_LAUNCH();
+  return 0;
+}
+
 // ---- element density and material interpolation ----------------------------------------------
 // rhoE[e] = 1/4 sum_a rho[conn[e, a]]          (examples/thermal.py:348-353, natural_frequency.py:399-404)
 // law 0 (thermal.py:132,198,175-188,236-244): ks = k0((1-b) r^p + b), ms = c0((1-b) r + b)

@@ -385,6 +385,10 @@ class BucklingQ4Problem:
         return self.base.scatter_to_nodes(evals, scale)
 
 
+def _contig1(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
 def to_host_i64(t):
     return t.detach().cpu().numpy().astype(np.int64)
 
@@ -392,8 +396,8 @@ def to_host_i64(t):
 class NodeFilter:
     """Conic node filter F[i, j] ~ max(0, r0 - |X_i - X_j|), rows normalised to 1
     (examples/node_filter.py:61-88), applied on the device as CSR products (:164-217).
-    Spatial filter with optional design-variable map (the symmetric column of examples/buckling.py:1331-1344),
-    without the tanh projection."""
+    Spatial filter with optional design-variable map (the symmetric column of examples/buckling.py:1331-1344)
+    and optional tanh projection (``projection=True``, ``beta``, ``eta``)."""
 
     ftype = "spatial"
 
@@ -402,8 +406,9 @@ class NodeFilter:
         from scipy import sparse, spatial
         if ftype != "spatial":
             raise NotImplementedError("only the spatial (conic) filter is implemented")
-        if projection:
-            raise NotImplementedError("the tanh projection is not implemented on the device filter")
+        self.projection = bool(projection)
+        self.beta = 10.0 if beta is None else float(beta)      # reference default (node_filter.py:30-31)
+        self.eta = float(eta)
         self.X = np.asarray(X, dtype=np.float64)
         self.nnodes = self.X.shape[0]
         self.r0 = r0
@@ -436,11 +441,28 @@ class NodeFilter:
         self.F_d = D.CsrDevice.from_scipy(F)
         self.FT_d = D.CsrDevice.from_scipy(FT)
 
-    def apply(self, x):
-        rho = self.F_d.spmm(to_dev(x))
+    def _filtered(self, x_d):
+        rho = self.F_d.spmm(x_d)
         if self.offset_d is not None:
             D.axpby(1.0, rho, 1.0, self.offset_d, out=rho)
+        return rho
+
+    def _project(self, rho, g=None):
+        out = D.empty(rho.shape[0])
+        _lib.check(_lib.load().eigd_filter_project(rho.shape[0], self.beta, self.eta, _ptr(rho), _ptr(g), _ptr(out)),
+                   "filter_project")
+        return out
+
+    def apply(self, x):
+        rho = self._filtered(to_dev(x))
+        if self.projection:                                    # node_filter.py:174-181
+            rho = self._project(rho)
         return like_input(rho, x)
 
     def apply_gradient(self, g, x=None, rho=None):
-        return like_input(self.FT_d.spmm(to_dev(g)), g)
+        g_d = to_dev(g)
+        if self.projection:                                    # node_filter.py:187-203: needs the unprojected field
+            if x is None:
+                raise ValueError("apply_gradient with projection needs the design x")
+            g_d = self._project(self._filtered(to_dev(x)), _contig1(g_d))
+        return like_input(self.FT_d.spmm(g_d), g)

@@ -171,6 +171,10 @@ int eigd_q4_material(int law, int nelems, const int* d_conn, const double* d_rho
 /* node_out[v] = scale * sum_{e in adj(v)} e_vals[e]   (gather form of np.add.at, thermal.py:612-615) */
 int eigd_node_gather(int nnodes, const int* d_nptr, const int* d_nelem, const double* d_evals, double scale, double* d_out);
 
+/* tanh projection of the filtered density (examples/node_filter.py:174-181) and its gradient factor (:193-203):
+ * d_g == NULL: out = projected rho; otherwise out = g * d(projection)/d(rho) evaluated at the UNPROJECTED rho */
+int eigd_filter_project(int n, double beta, double eta, const double* d_rho, const double* d_g, double* d_out);
+
 /* ---- linearised buckling (examples/buckling.py): stress stiffness G(u, x) and its sensitivities ---------
  * All vectors are in the FULL dof numbering (2 dof per node); eigd_expand_rows / eigd_reduce_rows are the
  * Dirichlet maps full_vector / reduce_vector (examples/buckling.py:499-518). */
