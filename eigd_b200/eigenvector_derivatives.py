@@ -1259,8 +1259,14 @@ class IRAM(_SolverBase):
         self.factor, self.A, self.B, self.sigma = factor, A, B, sigma
         self._Ad, self._Bd = as_csr_device(A), as_csr_device(B)
         A0 = self._Ad if self.mode == "normal" else self._Bd                                # :1938-1942
+        seed = self.seed
+        shard = getattr(self, "sharding", None)
+        if seed is None and shard is not None and shard.world > 1:
+            # replicated eigensolve: every rank must build the SAME basis (signs, rotations inside clusters), or
+            # the adjoint columns gathered from the other ranks belong to different eigenvectors
+            seed = 0
         lam, _, T, _, st = eigsh_mod(A0, M=self._Bd, OPinv=factor, k=self.N, sigma=sigma, which="LM", mode=self.mode,
-                                     tol=self.tol, ncv=self.m, return_state=True, seed=self.seed)
+                                     tol=self.tol, ncv=self.m, return_state=True, seed=seed)
         self.lam, self.T = lam, T
         self.lanczos_state = st
         self._V_d = st.Vt.T

@@ -223,8 +223,9 @@ class BucklingTopologyAnalysis:
     def __init__(self, fltr, conn, X, bcs, forces={}, E=1.0, nu=0.3, ptype_K="simp", ptype_M="simp", ptype_G="simp",
                  rho0_K=1e-6, rho0_M=1e-9, rho0_G=1e-9, p=3.0, q=5.0, density=1.0, sigma=3.0, N=10, m=None,
                  solver_type="IRAM", tol=0.0, rtol=1e-10, eig_atol=1e-5, adjoint_method="shift-invert",
-                 adjoint_options=None, cost=1, deriv_type="tensor"):
+                 adjoint_options=None, cost=1, deriv_type="tensor", seed=0):
         self.fltr = fltr
+        self.seed = seed                  # IRAM start vector (deterministic: the eigensolve is replicated when sharded)
         self.conn, self.X = np.asarray(conn), np.asarray(X)
         self.prob = fe.BucklingQ4Problem(self.conn, self.X, bcs, forces, E=E, nu=nu, density=density, p=float(p),
                                          q=float(q), rho0_K=rho0_K, rho0_G=rho0_G, ptype_K=ptype_K.lower(),
@@ -272,6 +273,7 @@ class BucklingTopologyAnalysis:
             if self.m is None:
                 self.m = max(2 * self.N + 1, 60)
             self.eig_solver = IRAM(N=self.N, m=self.m, eig_atol=self.eig_atol, mode="buckling")
+            self.eig_solver.seed = self.seed
         else:
             if self.m is None:
                 self.m = max(3 * self.N + 1, 60)

@@ -39,16 +39,34 @@ def residuals(model, A, B, lam, Phi_d, mode):
     return res, float(np.abs(G - np.eye(G.shape[0])).max())
 
 
+def setup_dist():
+    """torchrun launch: one process per GPU, per-mode adjoint shards (eigd_b200/dist.py)."""
+    import torch
+    import torch.distributed as dist
+    from eigd_b200 import device as D
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    D.init("cuda:%d" % local)
+    if world == 1:
+        return None, 0, 1
+    dist.init_process_group("nccl")
+    from eigd_b200.dist import ModeSharding
+    return ModeSharding(), dist.get_rank(), world
+
+
 def run_c3(args):
     from eigd_b200 import device as D, topo as T
-    D.init()
+    shard, rank, world = setup_dist()
     t0 = now()
     model = T.make_buckling_model(nx=args.nx, ny=args.ny, N=args.modes, m=60, sigma=3.0, solver_type="IRAM",
                                   adjoint_method="sibk", adjoint_options={"lanczos_guess": True}, rtol=1e-10,
                                   deriv_type="tensor")
     t_setup = now() - t0
+    model.sharding = shard
     out = {"config": "C3 buckling nx=%d ny=%d" % (args.nx, args.ny), "n": int(model.prob.nred), "nnz": int(model.prob.nnz),
-           "N": args.modes, "host_setup_s": t_setup}
+           "N": args.modes, "host_setup_s": t_setup, "n_gpus": world,
+           "parallelism": "1 GPU" if world == 1 else "eigensolve replicated, adjoint modes i -> rank i mod %d" % world}
     rng = np.random.default_rng(0)
     reps = []
     for rep in range(args.reps):
@@ -144,4 +162,5 @@ if __name__ == "__main__":
     else:
         a.nx, a.ny, a.modes, a.designs = a.nx or 1000, a.ny or 500, a.modes or 20, a.designs or 2
         res = run_nf(a, "C4 stand-in (1M-DOF 2-dof plate; the reference's shell model needs TACS)")
-    print(json.dumps(res))
+    if int(os.environ.get("RANK", "0")) == 0:
+        print(json.dumps(res))
