@@ -31,6 +31,12 @@ __all__ = ["SpLuOperator", "add_eig_total_derivative", "eval_adjoint_residual_no
 _SYMBOLIC_CACHE = {}
 
 
+def _is_complex_host(M):
+    """scipy sparse matrix with complex values (a complex-step operand); device matrices are always real"""
+    d = getattr(M, "data", None)
+    return isinstance(d, np.ndarray) and np.iscomplexobj(d)
+
+
 def _check_mode(mode):
     if mode not in ("normal", "buckling"):
         raise ValueError(f"Unknown mode {mode!r}")
@@ -54,19 +60,25 @@ class SpLuOperator:
     """
 
     def __init__(self, mat, coords=None, dof_per_node=1, symbolic=None, refine=None, max_rhs=32):
+        self.tangent = None
         if isinstance(mat, D.CsrDevice):
             csr = mat
         else:
             if not hasattr(mat, "tocsr"):
                 raise TypeError("SpLuOperator needs a scipy sparse matrix or a device.CsrDevice")
+            self.tangent = None
             if np.iscomplexobj(mat.data):
-                raise NotImplementedError("complex matrices (complex-step) are not supported on the device path")
-            csr = D.CsrDevice.from_scipy(mat, symmetric=True)   # symmetric: CSC arrays of mat are CSR arrays of mat
-            XFER["h2d"] += csr.uploaded_bytes
+                # complex-step operand: factor the real part, keep the imaginary part as the tangent matrix (dual.py)
+                from . import dual
+                csr, self.tangent = dual.split_csr(mat, symmetric=True)
+                XFER["h2d"] += 2 * csr.uploaded_bytes
+            else:
+                csr = D.CsrDevice.from_scipy(mat, symmetric=True)   # symmetric: CSC arrays of mat are CSR arrays of mat
+                XFER["h2d"] += csr.uploaded_bytes
         if csr.shape[0] != csr.shape[1]:
             raise ValueError("expected square matrix")
         self.shape = csr.shape
-        self.dtype = np.dtype(np.float64)
+        self.dtype = np.dtype(np.complex128 if self.tangent is not None else np.float64)
         self.count = 0
         self.mat = csr
         n = csr.shape[0]
@@ -144,6 +156,17 @@ class SpLuOperator:
         x = np.asarray(x)
         if x.shape[0] != self.shape[0] or x.ndim > 2:
             raise ValueError("dimension mismatch")
+        if self.tangent is not None or np.iscomplexobj(x):
+            # dual solve: A y = b, A dy = db - dA y (the imaginary parts are forward derivatives, dual.py)
+            xr = to_dev(np.ascontiguousarray(x.real))
+            yr = self.solve_dev(xr)
+            rhs = to_dev(np.ascontiguousarray(x.imag)) if np.iscomplexobj(x) else D.zeros(*x.shape)
+            if self.tangent is not None:
+                t = self.tangent.spmm(yr)
+                D.axpby(1.0, _contig(rhs).reshape(-1), -1.0, t.reshape(-1), out=t.reshape(-1))
+                rhs = t
+            self.count -= 1 if x.ndim == 1 else x.shape[1]
+            return to_host(yr) + 1j * to_host(self.solve_dev(rhs))
         return to_host(self.solve_dev(to_dev(x)))
 
     __call__ = _apply
@@ -1142,7 +1165,40 @@ class BasicLanczos(_SolverBase):
             indices = np.argsort(-1.0 / lam)
         return theta, Y, T, lam, indices
 
+    def _solve_dual(self, A, B, factor, sigma):
+        """Complex-step operands (reference :1483-1493 dtype switch): the recurrence in dual numbers (dual.py)."""
+        from . import dual
+        if self.ortho_type != "full":
+            raise NotImplementedError("complex-step operands are implemented for ortho_type='full'")
+        if getattr(factor, "tangent", None) is None:
+            raise ValueError("complex A, B need a SpLuOperator built from the complex shifted matrix")
+        z = lambda M: (dual.split_csr(M) if dual.is_complex_matrix(M) else
+                       (as_csr_device(M), as_csr_device(M).with_values(D.zeros(as_csr_device(M).nnz))))
+        (Ar, At), (Br, Bt) = z(A), z(B)
+        self.A, self.B, self.factor, self.sigma = A, B, factor, sigma
+        self._Ad, self._Bd = Ar, Br
+        res = dual.basic_lanczos(Ar, At, Br, Bt, factor, sigma, self.N, self.m_max, self.tol, self.Ntarget, self.mode)
+        m = self.m = res["m"]
+        self.alpha, self.beta = res["alpha"], res["beta"]
+        self.theta, self.Y, self.T, self.lam, self.indices = res["theta"], res["Y"], res["T"], res["lam"], res["indices"]
+        if self.Ntarget is not None:
+            self.N = self.Ntarget
+            while self.N < m and _is_close(self.lam[self.indices[self.N - 1]].real, self.lam[self.indices[self.N]].real,
+                                           self.eig_atol):
+                self.N += 1
+        self.lam0 = self.lam[self.indices[: self.N]]
+        self.Y0 = self.Y[:, self.indices[: self.N]]
+        self.eig_res = np.abs(self.beta[m - 1].real * self.Y0[m - 1, :].real)
+        self.fail = bool(np.any(self.eig_res >= max(self.tol, 1e-8)))
+        self.Phi = dual.ritz_vectors(res, self.indices[: self.N])
+        self._Phi_d = None
+        self._dual = res
+        self._V_host = np.stack([to_host(v.r) + 1j * to_host(v.t) for v in res["V"]], axis=1)
+        return self.lam0, self.Phi
+
     def solve(self, A, B, factor, sigma):
+        if _is_complex_host(A) or _is_complex_host(B):
+            return self._solve_dual(A, B, factor, sigma)
         n = self._common_solve_checks(A, B, factor)
         self.A, self.B, self.factor, self.sigma = A, B, factor, sigma
         self._Ad, self._Bd = as_csr_device(A), as_csr_device(B)

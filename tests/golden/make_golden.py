@@ -75,6 +75,27 @@ def thermal_case(solver_type, methods, nx=24, ny=20, N=6, m=30, seed=3):
                                             factor=topo.factor, rtol=1e-12, **kw)
             out["psi_sibk_free_" + tag] = psi_v.copy()
             out["info_sibk_free_" + tag] = np.array(info_v)
+        # complex-step run of the example (thermal.py:652-661): design x + i h pert -> complex K, M -> the reference's
+        # BasicLanczos treats the imaginary parts as forward derivatives; stored as tangents (imag / h)
+        hcs = 1e-30
+        x0 = topo.x.copy()
+        pert = np.random.default_rng(21).uniform(size=x0.shape)
+        topo.x = x0.astype(complex)
+        topo.x.imag += hcs * pert
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            topo.initialize()
+        Kc, Mc = topo.K.tocsr(), topo.M.tocsr()
+        Kc.sort_indices()
+        Mc.sort_indices()
+        out.update(dict(cs_pert=pert, cs_A_tan=Kc.data.imag / hcs, cs_B_tan=Mc.data.imag / hcs,
+                        cs_A_real=Kc.data.real.copy(), cs_lam=np.asarray(topo.lam).real.copy(),
+                        cs_lam_tan=np.asarray(topo.lam).imag / hcs, cs_Phi=topo.Q.real.copy(), cs_Phi_tan=topo.Q.imag / hcs,
+                        cs_m=topo.eig_solver.m))
+        topo.x = x0
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            topo.initialize()
         # BasicLanczos with selective orthogonalisation (eigd/eigenvector_derivatives.py:1553-1605) on the same pencil
         sel = rl.load_reference().BasicLanczos(N=N, m=es.m_max, tol=1e-14, ortho_type="selective")
         fsel = rl.load_reference().SpLuOperator((topo.K - topo.sigma * topo.M).tocsc())

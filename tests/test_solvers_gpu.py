@@ -295,3 +295,32 @@ def test_basic_lanczos_selective_orthogonalisation(E, th):
     assert rel(Pa, th["sel_Phi"]) < 1e-7          # selective orthogonalisation itself is only good to ~sqrt(tol) = 1e-7
     assert s.m == int(th["sel_m"])
     assert rel(s.alpha[:8], th["sel_alpha"][:8]) < 1e-10 and rel(s.beta[:8], th["sel_beta"][:8]) < 1e-10
+
+
+def test_complex_step_operands_basic_lanczos(E, th):
+    """Complex-step mode (examples/thermal.py:652-661): complex K, M (design perturbed by i h p) through SpLuOperator
+    and BasicLanczos; the imaginary parts are forward derivatives (reference :1387-1414).  Carried on the device as
+    dual numbers; compared with the reference's own complex run on the same matrices (tangent = imag / h)."""
+    import scipy.sparse as sp
+    h = 1e-30
+    A, B, sigma = th["A"], th["B"], float(th["sigma"])
+    Ac = sp.csr_matrix((A.data + 1j * h * th["cs_A_tan"], A.indices, A.indptr), shape=A.shape)
+    Bc = sp.csr_matrix((B.data + 1j * h * th["cs_B_tan"], B.indices, B.indptr), shape=B.shape)
+    f = E.SpLuOperator((Ac - sigma * Bc).tocsc())
+    assert f.dtype == np.complex128
+    s = E.BasicLanczos(N=int(th["N"]), m=int(th["m_max"]), tol=1e-14)
+    lam, Phi = s.solve(Ac, Bc, f, sigma)
+    assert np.iscomplexobj(lam) and np.iscomplexobj(Phi) and s.m == int(th["cs_m"])
+    scale = np.abs(th["cs_lam"]).max()
+    assert np.abs(lam.real - th["cs_lam"]).max() < 1e-10 * scale
+    assert np.abs(lam.imag / h - th["cs_lam_tan"]).max() < 1e-8 * np.abs(th["cs_lam_tan"]).max()
+    sgn = np.sign(np.einsum("ij,ij->j", Phi.real, th["cs_Phi"]))
+    assert rel(Phi.real * sgn, th["cs_Phi"]) < 1e-8
+    assert rel(Phi.imag / h * sgn, th["cs_Phi_tan"]) < 1e-6
+    # the complex operator itself: (A + i dA)(y + i dy) = b
+    rng = np.random.default_rng(2)
+    b = rng.normal(size=A.shape[0])
+    y = f(b)
+    mat = (Ac - sigma * Bc).tocsr()
+    r = mat @ y - b
+    assert np.abs(r.real).max() < 1e-10 and np.abs(r.imag).max() < 1e-10 * h * 1e3 + 1e-38
