@@ -31,6 +31,9 @@ def as_csr_device(A):
     if base is not None and hasattr(base, "tocsr"):
         A = base
     if hasattr(A, "tocsr"):
+        if np.iscomplexobj(getattr(A, "data", 0.0)):
+            raise NotImplementedError("eigd_b200: complex (complex-step) matrices are supported by SpLuOperator and "
+                                      "BasicLanczos.solve only (eigd_b200/dual.py), as in the reference's own checks")
         out = D.CsrDevice.from_scipy(A)
         XFER["h2d"] += out.uploaded_bytes
         return out

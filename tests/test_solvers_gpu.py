@@ -324,3 +324,12 @@ def test_complex_step_operands_basic_lanczos(E, th):
     mat = (Ac - sigma * Bc).tocsr()
     r = mat @ y - b
     assert np.abs(r.real).max() < 1e-10 and np.abs(r.imag).max() < 1e-10 * h * 1e3 + 1e-38
+
+
+def test_complex_operands_outside_basic_lanczos_raise(E, th):
+    import scipy.sparse as sp
+    A, B, sigma = th["A"], th["B"], float(th["sigma"])
+    Ac = sp.csr_matrix((A.data + 1e-30j * th["cs_A_tan"], A.indices, A.indptr), shape=A.shape)
+    f = E.SpLuOperator((A - sigma * B).tocsc())
+    with pytest.raises(NotImplementedError):
+        E.IRAM(N=4, m=20).solve(Ac, B, f, sigma)
