@@ -6,3 +6,4 @@ Public surface mirrors the reference's ``eigd`` package (eigd/__init__.py:1-3): 
 __version__ = "1.0.0"
 
 from .eigenvector_derivatives import *  # noqa: F401,F403
+from .device import pinned_empty  # noqa: E402,F401  (page-locked numpy arrays for the fastest uploads)

@@ -50,12 +50,12 @@ def to_dev(x, copy=False):
     if np.iscomplexobj(a):
         raise NotImplementedError("eigd_b200: complex (complex-step) operands are not supported on the device path")
     XFER["h2d"] += a.size * 8
-    return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device=D.dev())
+    return D.h2d(np.ascontiguousarray(a, dtype=np.float64))
 
 
 def to_host(t):
     XFER["d2h"] += t.numel() * t.element_size()
-    return t.detach().cpu().numpy()
+    return D.d2h(t)
 
 
 def like_input(t, ref):

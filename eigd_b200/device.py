@@ -8,6 +8,8 @@ every call raises.
 """
 import ctypes
 import hashlib
+import time
+import warnings
 
 import numpy as np
 
@@ -114,12 +116,106 @@ def launch_count():
     return int(_lib.load().eigd_launch_count())
 
 
+# Host <-> device copies of the numpy API.  Arrays of a megabyte or more travel through page-locked memory:
+# uploads are staged (host copy into a block of torch's caching pinned allocator -- or not at all
+# when the caller's array already is page-locked, see ``pinned_empty``) and issued on a copy stream, so that they
+# overlap kernels already queued on the compute stream (the factorisation while K and M upload); downloads land
+# in a pinned block that the returned numpy array views directly (no second host copy).
+_BIG_COPY = 1 << 20
+
+
+class _Copy:
+    stream = None
+
+
+def _copy_stream():
+    if _Copy.stream is None:
+        _Copy.stream = torch.cuda.Stream(device=dev())
+    return _Copy.stream
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """numpy array in page-locked host memory (uploads from it skip the staging copy)."""
+    dev()
+    t = torch.empty(tuple(int(v) for v in np.atleast_1d(shape)), dtype=torch.from_numpy(np.empty(0, dtype=dtype)).dtype,
+                    pin_memory=True)
+    return t.numpy()
+
+
+COPY_STATS = {}     # developer counters: piece -> [calls, seconds, bytes] (tools/prof_e2e.py prints them)
+
+
+def _stat(key, t0, nbytes):
+    c = COPY_STATS.setdefault(key, [0, 0.0, 0])
+    c[0] += 1
+    c[1] += time.perf_counter() - t0
+    c[2] += nbytes
+
+
+def h2d(a):
+    """contiguous numpy array -> CUDA tensor of the same dtype, ordered before later work on the current stream."""
+    d = dev()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")            # read-only numpy arrays: we only read
+        if a.nbytes < _BIG_COPY:
+            return torch.as_tensor(a, device=d)
+        src = torch.from_numpy(a)
+    own = src.is_pinned()
+    if own:
+        stage = src
+    else:
+        t0 = time.perf_counter()
+        stage = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
+        _stat("h2d pinned block", t0, 0)
+        t0 = time.perf_counter()
+        # single-threaded on purpose: torch's OpenMP copy_ measured 2.6-6 GB/s here inside a gradient step on a
+        # shared host (104 GB/s in a cache-warm microbenchmark), numpy's memcpy is steady (tools/time_copies.py)
+        np.copyto(stage.numpy(), a)
+        _stat("h2d staging copy", t0, a.nbytes)
+    t0 = time.perf_counter()
+    cs, main = _copy_stream(), torch.cuda.current_stream(d)
+    with torch.cuda.stream(cs):
+        out = stage.to(d, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(cs)
+    main.wait_event(ev)
+    out.record_stream(main)
+    _stat("h2d issue", t0, a.nbytes)
+    if own:
+        t0 = time.perf_counter()
+        ev.synchronize()                            # the caller may overwrite its array once we return
+        _stat("h2d wait (caller's pinned array)", t0, a.nbytes)
+    return out
+
+
+def d2h(t):
+    """CUDA tensor -> numpy array (same strides for dense tensors, as ``Tensor.cpu``)."""
+    t = t.detach()
+    if not t.is_cuda or t.numel() * t.element_size() < _BIG_COPY:
+        t0 = time.perf_counter()
+        out = t.cpu().numpy()
+        _stat("d2h small (.cpu, includes waiting for the GPU)", t0, out.nbytes)
+        return out
+    t0 = time.perf_counter()
+    stage = torch.empty_like(t, device="cpu", pin_memory=True)
+    _stat("d2h pinned block", t0, 0)
+    t0 = time.perf_counter()
+    stage.copy_(t, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(t.device))
+    _stat("d2h issue", t0, 0)
+    t0 = time.perf_counter()
+    ev.synchronize()
+    _stat("d2h wait (includes waiting for the GPU)", t0, stage.numel() * stage.element_size())
+    return stage.numpy()
+
+
 def to_device(x, dtype=F64):
     """numpy / torch -> CUDA tensor (no copy if already there)."""
     d = dev()
     if isinstance(x, torch.Tensor):
         return x.to(device=d, dtype=dtype)
-    return torch.as_tensor(np.ascontiguousarray(x), device=d).to(dtype)
+    return h2d(np.ascontiguousarray(x)).to(dtype)
 
 
 def empty(*shape):
@@ -395,16 +491,26 @@ class PatternCache:
 
     @classmethod
     def get(cls, indptr, indices):
-        """-> (entry id, device indptr, device indices); arrays must be int32, contiguous, sorted rows."""
+        """-> (entry id, device indptr, device indices, fresh); arrays must be int32, contiguous, sorted rows.
+
+        The full comparison costs a pass over both arrays (3 ms per gradient at C2 for K, M and K - sigma*M), so
+        an entry also remembers the array *objects* it was last confirmed against: the same objects with an
+        unchanged fingerprint are accepted without the pass (index arrays of an assembled FE matrix are not edited
+        in place; scipy operations return new arrays, which take the full comparison)."""
         fp = cls._fingerprint(indptr, indices)
         for ent in cls._entries.get(fp, []):
-            if np.array_equal(ent[1], indptr) and np.array_equal(ent[2], indices):
+            seen = ent[5]
+            if any(a is indptr and b is indices for a, b in seen):
                 return ent[0], ent[3], ent[4], False
-        d = dev()
+            if np.array_equal(ent[1], indptr) and np.array_equal(ent[2], indices):
+                if len(seen) >= 8:
+                    del seen[0]
+                seen.append((indptr, indices))
+                return ent[0], ent[3], ent[4], False
         if sum(len(v) for v in cls._entries.values()) > 16:
             cls._entries.clear()
         eid = "p%d_%d_%d" % (fp[0], fp[1], id(indices))
-        ent = (eid, indptr.copy(), indices.copy(), torch.as_tensor(indptr, device=d), torch.as_tensor(indices, device=d))
+        ent = (eid, indptr.copy(), indices.copy(), h2d(indptr), h2d(indices), [(indptr, indices)])
         cls._entries.setdefault(fp, []).append(ent)
         return eid, ent[3], ent[4], True
 

@@ -209,3 +209,53 @@ def test_q4_kernels(D, kind, N):
     nd = D.empty(mdl.nnodes)
     D.node_gather(torch.as_tensor(nptr, device=D.dev()), torch.as_tensor(nelem, device=D.dev()), D.to_device(ev), 0.25, nd)
     assert rel(nd.cpu().numpy(), mdl.scatter_to_nodes(ev)) < 1e-13
+
+
+def test_host_device_copies(D):
+    """Copies behind the numpy API: pageable, read-only and page-locked sources, transposed / sliced device
+    tensors, sizes either side of the pinned-path threshold -- all bit-exact round trips."""
+    rng = np.random.default_rng(5)
+    for shape in [(7,), (300, 10), (200_000, 3), (150_000, 10)]:
+        a = rng.standard_normal(shape)
+        t = D.h2d(a)
+        assert t.is_cuda and tuple(t.shape) == shape
+        assert np.array_equal(D.d2h(t), a)
+        ro = a.copy()
+        ro.setflags(write=False)
+        assert np.array_equal(D.d2h(D.h2d(ro)), a)
+        p = D.pinned_empty(shape)
+        p[...] = a
+        tp = D.h2d(p)
+        p[...] = 0.0                                  # the upload must be complete when h2d returns
+        assert np.array_equal(D.d2h(tp), a)
+    big = D.h2d(rng.standard_normal((150_000, 10)))
+    back = D.d2h(big.T)                               # dense, transposed: strides preserved like Tensor.cpu()
+    assert back.shape == (10, 150_000) and np.array_equal(back, big.cpu().numpy().T)
+    sl = D.d2h(big[:, 2:9])                           # non-dense view
+    assert np.array_equal(sl, big.cpu().numpy()[:, 2:9])
+    out = D.d2h(big)
+    out[0, 0] = 123.0                                 # returned arrays are writable and independent of the device copy
+    assert float(big[0, 0]) != 123.0
+    idx = rng.integers(0, 1000, 600_000).astype(np.int32)
+    assert np.array_equal(D.d2h(D.h2d(idx)), idx)
+
+
+def test_pattern_cache_identity_and_change(D):
+    """The CSR structure is uploaded once per pattern; the same arrays are accepted again, edited or different
+    arrays are compared in full (a changed pattern must never be served from the cache)."""
+    rng = np.random.default_rng(9)
+    A, _ = grid_matrix(41, 29, 1, rng)
+    c1 = D.CsrDevice.from_scipy(A)
+    c2 = D.CsrDevice.from_scipy(A)                    # identical objects -> identity path
+    assert c2.indices.data_ptr() == c1.indices.data_ptr()
+    B = A.copy()                                      # new arrays, same pattern -> full comparison, same entry
+    c3 = D.CsrDevice.from_scipy(B)
+    assert c3.indices.data_ptr() == c1.indices.data_ptr()
+    C = A.copy()
+    r = C.shape[0] // 2
+    lo, hi = C.indptr[r], C.indptr[r + 1]
+    C.indices[lo:hi] = np.sort((C.indices[lo:hi] + 3) % C.shape[1])    # same sizes, different columns
+    c4 = D.CsrDevice.from_scipy(C)
+    assert np.array_equal(c4.indices.cpu().numpy(), C.indices)
+    x = rng.standard_normal(C.shape[1])
+    assert rel(c4.spmm(D.to_device(x)).cpu().numpy(), C @ x) < 1e-13

@@ -13,6 +13,9 @@ vec_h = np.random.default_rng(12345).uniform(size=model.nnodes)
 model.initialize(x=x_d)
 K_h, M_h = model.K.to_scipy(), model.M.to_scipy()
 mat_h = (K_h - SIGMA * M_h).tocsc()
+if "--pinned" in sys.argv:
+    for A_h in (K_h, M_h, mat_h):
+        vals = D.pinned_empty(A_h.data.shape); vals[...] = A_h.data; A_h.data = vals
 prob = model.prob
 
 def step():
@@ -20,7 +23,7 @@ def step():
     s = E.IRAM(N=N, m=60); s.seed = 0
     lam, Phi = s.solve(K_h, M_h, f, SIGMA)
     c = Phi.T @ vec_h
-    Phib = 2.0 * np.outer(vec_h, c / lam); lamb = -(c * c) / lam**2
+    Phib = np.outer(vec_h, 2.0 * c / lam); lamb = -(c * c) / lam**2
     Phib[:, 0], lamb[0] = 0.0, 0.0
     psi, data = s.solve_adjoint(Phib, method="sibk", rtol=1e-10, lanczos_guess=True)
     dfdx = np.zeros(prob.nelems)
@@ -29,9 +32,13 @@ def step():
     return dfdx
 
 for _ in range(3): step()
+D.COPY_STATS.clear()
 t0 = time.perf_counter()
 for _ in range(3): step()
 print("e2e step %.1f ms" % ((time.perf_counter() - t0) / 3 * 1e3))
+for k, (c, sec, nb) in D.COPY_STATS.items():
+    print("  %-52s %5.1f calls/step %7.2f ms/step %7.1f MB/step" % (k, c / 3, sec / 3 * 1e3, nb / 3 / 1e6))
+if "--no-cprofile" in sys.argv: sys.exit(0)
 pr = cProfile.Profile(); pr.enable()
 for _ in range(3): step()
 pr.disable()
