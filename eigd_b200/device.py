@@ -168,8 +168,9 @@ def h2d(a):
         stage = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
         _stat("h2d pinned block", t0, 0)
         t0 = time.perf_counter()
-        # single-threaded on purpose: torch's OpenMP copy_ measured 2.6-6 GB/s here inside a gradient step on a
-        # shared host (104 GB/s in a cache-warm microbenchmark), numpy's memcpy is steady (tools/time_copies.py)
+        # single-threaded on purpose: inside a gradient step this host copies cold data at about 10 GB/s whatever
+        # the thread count (4 Python threads: 9.5 vs 9.1 ms per 96 MB), and torch's OpenMP copy_ fell to 2.6-6 GB/s
+        # there (104 GB/s in a cache-warm microbenchmark, tools/time_copies.py)
         np.copyto(stage.numpy(), a)
         _stat("h2d staging copy", t0, a.nbytes)
     t0 = time.perf_counter()
