@@ -1172,7 +1172,7 @@ class BasicLanczos(_SolverBase):
         self.N, self.m_max, self.tol, self.Ntarget = N, m, tol, Ntarget
         self.eig_atol, self.mode, self.ortho_type = eig_atol, mode, ortho_type
         self.m = m
-        self._Phi_d = self._Phi_host_sig = None
+        self._Phi_d = self._Phi_host_sig = self._Phib_last = None
 
     def _solve_reduced_problem(self, alpha, beta, sigma, m):
         T = np.diag(alpha[:m]) + np.diag(beta[: m - 1], 1) + np.diag(beta[: m - 1], -1)     # :1416-1439
@@ -1328,7 +1328,7 @@ class IRAM(_SolverBase):
         _check_mode(mode)
         self.mode = mode
         self.seed = None          # start-vector seed (scipy >= 1.15 draws it at random; None keeps that)
-        self._Phi_d = self._Phi_host_sig = None
+        self._Phi_d = self._Phi_host_sig = self._Phib_last = None
 
     def solve(self, A, B, factor, sigma):
         n = self._common_solve_checks(A, B, factor)

@@ -18,26 +18,34 @@ if "--pinned" in sys.argv:
         vals = D.pinned_empty(A_h.data.shape); vals[...] = A_h.data; A_h.data = vals
 prob = model.prob
 
+Phib_pin = D.pinned_empty((model.nnodes, N)) if "--pinned" in sys.argv else None
+STAMPS = {}
+
+
 def step():
-    f = E.SpLuOperator(mat_h, coords=model.X, dof_per_node=1)
+    t = [time.perf_counter()]
+    f = E.SpLuOperator(mat_h, coords=model.X, dof_per_node=1); t.append(time.perf_counter())
     s = E.IRAM(N=N, m=60); s.seed = 0
-    lam, Phi = s.solve(K_h, M_h, f, SIGMA)
+    lam, Phi = s.solve(K_h, M_h, f, SIGMA); t.append(time.perf_counter())
     c = Phi.T @ vec_h
-    Phib = np.outer(vec_h, 2.0 * c / lam); lamb = -(c * c) / lam**2
-    Phib[:, 0], lamb[0] = 0.0, 0.0
-    psi, data = s.solve_adjoint(Phib, method="sibk", rtol=1e-10, lanczos_guess=True)
+    Phib = np.multiply.outer(vec_h, 2.0 * c / lam, out=Phib_pin); lamb = -(c * c) / lam**2
+    Phib[:, 0], lamb[0] = 0.0, 0.0; t.append(time.perf_counter())
+    psi, data = s.solve_adjoint(Phib, method="sibk", rtol=1e-10, lanczos_guess=True); t.append(time.perf_counter())
     dfdx = np.zeros(prob.nelems)
     s.add_total_derivative(lamb, Phib, psi, prob.dAdx, prob.dBdx, dfdx, adj_corr_data=data, deriv_type="tensor")
-    torch.cuda.synchronize()
+    t.append(time.perf_counter())
+    for k, a, b in zip(("SpLuOperator", "solve", "host Phib", "solve_adjoint", "add_total_derivative"), t, t[1:]):
+        STAMPS[k] = STAMPS.get(k, 0.0) + (b - a)
     return dfdx
 
 for _ in range(3): step()
-D.COPY_STATS.clear()
+D.COPY_STATS.clear(); STAMPS.clear()
 t0 = time.perf_counter()
 for _ in range(3): step()
 print("e2e step %.1f ms" % ((time.perf_counter() - t0) / 3 * 1e3))
 for k, (c, sec, nb) in D.COPY_STATS.items():
     print("  %-52s %5.1f calls/step %7.2f ms/step %7.1f MB/step" % (k, c / 3, sec / 3 * 1e3, nb / 3 / 1e6))
+print("  host wall clock per call: " + ", ".join("%s %.2f ms" % (k, v / 3 * 1e3) for k, v in STAMPS.items()))
 if "--no-cprofile" in sys.argv: sys.exit(0)
 pr = cProfile.Profile(); pr.enable()
 for _ in range(3): step()
