@@ -28,6 +28,7 @@ SIGNATURES = {
     "eigd_gemm_nn": (c_int, [c_i64, c_int, c_int, c_dbl, c_ptr, c_i64, c_i64, c_ptr, c_int, c_dbl, c_ptr, c_i64, c_i64]),
     "eigd_col_dot": (c_int, [c_i64, c_int, c_ptr, c_i64, c_i64, c_ptr, c_i64, c_i64, c_ptr, c_ptr]),
     "eigd_col_axpy": (c_int, [c_i64, c_int, c_dbl, c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_i64, c_i64]),
+    "eigd_mgs_sweep": (c_int, [c_i64, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr]),
     "eigd_col_scale": (c_int, [c_i64, c_int, c_int, c_ptr, c_ptr, c_i64, c_i64]),
     "eigd_copy2d": (c_int, [c_i64, c_int, c_ptr, c_i64, c_i64, c_ptr, c_i64, c_i64]),
     "eigd_symbolic_create": (c_int, [c_int, c_ptr, c_ptr, c_ptr, c_int, c_int, c_ptr, c_ptr]),

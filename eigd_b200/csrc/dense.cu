@@ -532,6 +532,137 @@ extern "C" int eigd_col_dot(int64_t n, int k, const double* X, int64_t xrs, int6
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Modified Gram-Schmidt sweep of a block of k columns (the k adjoint systems in lock step) against j stored
+// blocks, in ONE cooperative launch:   for t = 0 .. j-1:  h_t[c] = sum_i w[i,c] W_t[i,c];  w[:,c] -= h_t[c] W_t[:,c]
+// (reference eigd/eigenvector_derivatives.py:1254-1257 and :1012-1014: one dot / axpy pair per stored vector).
+// Every CTA owns a fixed range of rows, so only the k dot products cross CTAs: one software grid barrier per
+// stored block; the axpy with W_t and the partial dots with W_{t+1} share one pass over the CTA's rows of w
+// (which stay in L2), W_{t+1} is the only stream from HBM.  Partial sums are combined in a fixed order
+// (bitwise reproducible); the two halves of `partial` alternate so that a fast CTA never overwrites sums a slow
+// one is still reading (to write the sums of step t + 2 it must have passed barrier t + 1).
+constexpr int MGS_MAX = 64;     // stored blocks per launch (kernel-parameter space)
+constexpr int MGS_KMAX = 64;
+
+struct MgsArgs {
+  const double* W[MGS_MAX];
+  double* H[MGS_MAX];
+};
+
+__device__ __forceinline__ void mgs_grid_barrier(unsigned long long* ctr, unsigned long long target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long v;
+    asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(ctr) : "memory");
+    do {
+      asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(ctr) : "memory");
+    } while (v < target);
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256)
+mgs_sweep_kernel(int64_t n, int k, int j, MgsArgs a, double* __restrict__ w, double* __restrict__ partial,
+                 unsigned long long* ctr, unsigned long long base) {
+  __shared__ double red[256];
+  __shared__ double hs[MGS_KMAX];
+  const int G = gridDim.x;
+  const int RG = 256 / k;                                   // row lanes per column
+  const int rr = threadIdx.x / k, c = threadIdx.x - rr * k;
+  const bool on = rr < RG;
+  const int64_t per = (n + G - 1) / G;
+  const int64_t r0 = (int64_t)blockIdx.x * per;
+  const int64_t r1 = r0 + per < n ? r0 + per : n;
+  double acc = 0.0;
+  if (on) {
+    const double* W0 = a.W[0];
+    for (int64_t i = r0 + rr; i < r1; i += RG) acc = fma(w[i * k + c], __ldg(W0 + i * k + c), acc);
+  }
+  for (int t = 0; t < j; ++t) {
+    red[threadIdx.x] = on ? acc : 0.0;
+    __syncthreads();
+    double* mine = partial + ((int64_t)(t & 1) * G + blockIdx.x) * k;
+    if (threadIdx.x < k) {
+      double s = 0.0;
+      for (int g = 0; g < RG; ++g) s += red[g * k + threadIdx.x];
+      mine[threadIdx.x] = s;
+    }
+    mgs_grid_barrier(ctr, base + (unsigned long long)(t + 1) * (unsigned long long)G);
+    const double* all = partial + (int64_t)(t & 1) * G * k;
+    double s = 0.0;
+    if (on)
+      for (int g = rr; g < G; g += RG) s += __ldcg(all + (int64_t)g * k + c);
+    red[threadIdx.x] = on ? s : 0.0;
+    __syncthreads();
+    if (threadIdx.x < k) {
+      double h = 0.0;
+      for (int g = 0; g < RG; ++g) h += red[g * k + threadIdx.x];
+      hs[threadIdx.x] = h;
+      if (blockIdx.x == 0) a.H[t][threadIdx.x] = h;
+    }
+    __syncthreads();
+    acc = 0.0;
+    if (on) {
+      const double h = hs[c];
+      const double* Wt = a.W[t];
+      if (t + 1 < j) {
+        const double* Wn = a.W[t + 1];
+        for (int64_t i = r0 + rr; i < r1; i += RG) {
+          const int64_t e = i * k + c;
+          const double v = fma(-h, __ldg(Wt + e), w[e]);
+          w[e] = v;
+          acc = fma(v, __ldg(Wn + e), acc);
+        }
+      } else {
+        for (int64_t i = r0 + rr; i < r1; i += RG) {
+          const int64_t e = i * k + c;
+          w[e] = fma(-h, __ldg(Wt + e), w[e]);
+        }
+      }
+    }
+  }
+}
+
+static unsigned long long* g_mgs_ctr = nullptr;
+static unsigned long long g_mgs_base = 0;
+static int g_mgs_dev = -1, g_mgs_max_grid = 0;
+
+extern "C" int eigd_mgs_sweep(int64_t n, int k, int j, const double* const* W, double* const* H, double* d_w,
+                              double* d_work) {
+  if (n <= 0 || j <= 0) return 0;
+  if (k < 1 || k > MGS_KMAX) { eigd_set_error("mgs_sweep: k = %d outside 1..%d", k, MGS_KMAX); return 7; }
+  int dev = 0;
+  EIGD_CUDA(cudaGetDevice(&dev));
+  if (dev != g_mgs_dev) {
+    int sms = 0, occ = 0;
+    EIGD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    EIGD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mgs_sweep_kernel, 256, 0));
+    if (occ < 1) { eigd_set_error("mgs_sweep: kernel does not fit on an SM"); return 7; }
+    g_mgs_max_grid = sms * (occ < 2 ? occ : 2);
+    if (g_mgs_max_grid > RED_MAX_CTAS) g_mgs_max_grid = RED_MAX_CTAS;
+    EIGD_CUDA(cudaMalloc(&g_mgs_ctr, sizeof(unsigned long long)));
+    EIGD_CUDA(cudaMemsetAsync(g_mgs_ctr, 0, sizeof(unsigned long long), g_eigd_stream));
+    g_mgs_base = 0;
+    g_mgs_dev = dev;
+  }
+  const int RG = 256 / k;
+  int64_t want = (n + (int64_t)RG * 4 - 1) / ((int64_t)RG * 4);
+  int grid = (int)(want < 1 ? 1 : (want > g_mgs_max_grid ? g_mgs_max_grid : want));
+  for (int j0 = 0; j0 < j; j0 += MGS_MAX) {
+    const int jj = j - j0 < MGS_MAX ? j - j0 : MGS_MAX;
+    MgsArgs a;
+    for (int t = 0; t < jj; ++t) { a.W[t] = W[j0 + t]; a.H[t] = H[j0 + t]; }
+    for (int t = jj; t < MGS_MAX; ++t) { a.W[t] = nullptr; a.H[t] = nullptr; }
+    int64_t n_ = n; int k_ = k, jj_ = jj;
+    unsigned long long base = g_mgs_base;
+    void* params[] = {(void*)&n_, (void*)&k_, (void*)&jj_, (void*)&a, (void*)&d_w, (void*)&d_work, (void*)&g_mgs_ctr, (void*)&base};
+    EIGD_CUDA(cudaLaunchCooperativeKernel((void*)mgs_sweep_kernel, dim3(grid), dim3(256), params, 0, g_eigd_stream));
+    ++g_eigd_launches;
+    g_mgs_base += (unsigned long long)jj * (unsigned long long)grid;
+  }
+  return 0;
+}
+
 static inline int ew_grid(int64_t total) {
   int64_t g = (total + 255) / 256;
   return (int)(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g));

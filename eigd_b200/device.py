@@ -359,6 +359,28 @@ def col_dot(X, Y, out=None):
     return out
 
 
+def mgs_sweep(w, Ws, Hs):
+    """Modified Gram-Schmidt of the columns of w (n, k) against the blocks Ws in the order given, coefficients of
+    block t into Hs[t] (k doubles): one cooperative launch instead of a dot / axpy pair per block."""
+    j = len(Ws)
+    if j == 0:
+        return w
+    n, k = w.shape
+    flat = k <= 64 and w.is_contiguous() and all(tuple(W.shape) == (n, k) and W.is_contiguous() for W in Ws) \
+        and all(h.numel() == k and h.is_contiguous() for h in Hs)
+    if not flat:
+        for W, h in zip(Ws, Hs):
+            col_dot(w, W, out=h)
+            col_axpy(w, h, W, sign=-1.0)
+        return w
+    _chk(w)
+    Wp = (ctypes.c_void_p * j)(*[_chk(W).data_ptr() for W in Ws])
+    Hp = (ctypes.c_void_p * j)(*[_chk(h).data_ptr() for h in Hs])
+    check(_lib.load().eigd_mgs_sweep(n, k, j, ctypes.cast(Wp, ctypes.c_void_p), ctypes.cast(Hp, ctypes.c_void_p),
+                                     _ptr(w), _ptr(_State.work)), "mgs_sweep")
+    return w
+
+
 def col_axpy(Y, s, X, sign=1.0):
     """Y[:, c] += sign * s[c] * X[:, c]"""
     X2, Y2 = _as2d(_chk(X)), _as2d(_chk(Y))

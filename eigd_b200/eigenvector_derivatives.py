@@ -698,9 +698,8 @@ def _sibk_dev(Phib_d, Ad, Bd, lam, Phi_d, mode, psi_d, sigma, factor, rtol, atol
         Z.append(factor.solve_dev(W[j - 1]))                                      # :1248
         w = opmat.spmm(Z[j - 1])                                                  # :1250-1252
         _project(BPhi, Phi_d, w)
-        for k in range(j - 1, -1, -1):                                            # modified Gram-Schmidt, descending (:1254-1257)
-            D.col_dot(w, W[k], out=hdev[k])
-            D.col_axpy(w, hdev[k], W[k], sign=-1.0)
+        ks = range(j - 1, -1, -1)                                                 # modified Gram-Schmidt, descending (:1254-1257)
+        D.mgs_sweep(w, [W[k] for k in ks], [hdev[k] for k in ks])
         _project(BPhi, Phi_d, w)                                                  # :1258
         D.col_dot(w, w, out=hdev[j])
         D.col_scale(w, hdev[j], mode=3)                                           # :1259-1260
@@ -964,9 +963,7 @@ def _pgmres_dev(Phib_d, Ad, Bd, lam, Phi_d, mode, psi_d, factor, rtol, atol, max
         Z.append(factor.solve_dev(t))                                             # :1003
         w = _apply_L(Ad, Bd, lam_d, Z[j], mode)
         _project(BPhi, Phi_d, w)                                                  # :1004-1010
-        for k in range(j + 1):                                                    # MGS ascending (:1012-1014)
-            D.col_dot(w, W[k], out=hdev[k])
-            D.col_axpy(w, hdev[k], W[k], sign=-1.0)
+        D.mgs_sweep(w, W[: j + 1], [hdev[k] for k in range(j + 1)])               # MGS ascending (:1012-1014)
         D.col_dot(w, w, out=hdev[j + 1])
         D.col_scale(w, hdev[j + 1], mode=3)
         W.append(w)

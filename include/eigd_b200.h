@@ -60,6 +60,12 @@ int eigd_col_dot(int64_t n, int k, const double* d_X, int64_t xrs, int64_t xcs,
 /* Y[i,c] += sign * s[c] * X[i,c]   (s on device) */
 int eigd_col_axpy(int64_t n, int k, double sign, const double* d_s, const double* d_X, int64_t xrs, int64_t xcs,
                   double* d_Y, int64_t yrs, int64_t ycs);
+/* Modified Gram-Schmidt sweep of the k columns of w (n x k, row-major, contiguous) against j stored blocks of the same
+ * layout, in the order given: h_t[c] = sum_i w[i,c] W_t[i,c]; w[:,c] -= h_t[c] W_t[:,c]; h_t is written to H[t] (k
+ * doubles on the device).  W and H are HOST arrays of j device pointers.  One cooperative launch per 64 blocks.
+ * Replaces the dot / axpy loops of eigd/eigenvector_derivatives.py:1254-1257 (sibk) and :1012-1014 (pgmres).
+ * d_work: the eigd_gemm_tn_workspace buffer.  k <= 64. */
+int eigd_mgs_sweep(int64_t n, int k, int j, const double* const* W, double* const* H, double* d_w, double* d_work);
 /* X[i,c] *= s[c]  (mode 0)   or   X[i,c] /= s[c]  (mode 1)   or X[i,c] /= sqrt(s[c]) (mode 2);
  * modes 3 / 4 are the zero-safe forms of 2 / 1 (a zero scale leaves a zero column) */
 int eigd_col_scale(int64_t n, int k, int mode, const double* d_s, double* d_X, int64_t xrs, int64_t xcs);

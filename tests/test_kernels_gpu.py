@@ -259,3 +259,33 @@ def test_pattern_cache_identity_and_change(D):
     assert np.array_equal(c4.indices.cpu().numpy(), C.indices)
     x = rng.standard_normal(C.shape[1])
     assert rel(c4.spmm(D.to_device(x)).cpu().numpy(), C @ x) < 1e-13
+
+
+@pytest.mark.parametrize("n,k,j", [(5003, 1, 3), (5003, 10, 7), (40_000, 10, 12), (251_001, 10, 9), (3001, 20, 5),
+                                   (777, 64, 2), (100_000, 3, 70), (50, 10, 4)])
+def test_mgs_sweep(D, n, k, j):
+    """One cooperative launch = the reference's dot / axpy loop over the stored blocks (sequential, modified GS)."""
+    rng = np.random.default_rng(n + k + j)
+    w = rng.normal(size=(n, k))
+    Ws = [rng.normal(size=(n, k)) / np.sqrt(n) for _ in range(j)]
+    ref, hs = w.copy(), []
+    for W in Ws:
+        h = np.einsum("ij,ij->j", ref, W)
+        ref -= h * W
+        hs.append(h)
+    wd = D.to_device(w)
+    H = D.zeros(j + 1, k)
+    D.mgs_sweep(wd, [D.to_device(W) for W in Ws], [H[t] for t in range(j)])
+    assert rel(wd.cpu().numpy(), ref) < 1e-13
+    assert rel(H[:j].cpu().numpy(), np.array(hs)) < 1e-12
+    assert float(H[j].abs().max()) == 0.0
+    # bitwise reproducible
+    wd2 = D.to_device(w)
+    H2 = D.zeros(j + 1, k)
+    D.mgs_sweep(wd2, [D.to_device(W) for W in Ws], [H2[t] for t in range(j)])
+    assert torch.equal(wd, wd2) and torch.equal(H, H2)
+    # non-contiguous operands take the dot / axpy path with the same result
+    wt = D.to_device(np.ascontiguousarray(w.T)).T
+    H3 = D.zeros(j, k)
+    D.mgs_sweep(wt, [D.to_device(W) for W in Ws], [H3[t] for t in range(j)])
+    assert rel(wt.cpu().numpy(), ref) < 1e-13
