@@ -8,6 +8,7 @@
 // shared memory with the unit-stride index varying fastest across the warp, so global loads
 // are coalesced for either layout.  Reductions over n are two-stage and deterministic.
 #include "common.cuh"
+#include <cstdlib>
 #include "../../include/eigd_b200.h"
 
 cudaStream_t g_eigd_stream = 0;
@@ -574,9 +575,19 @@ mgs_sweep_kernel(int64_t n, int k, int j, MgsArgs a, double* __restrict__ w, dou
   const int64_t r0 = (int64_t)blockIdx.x * per;
   const int64_t r1 = r0 + per < n ? r0 + per : n;
   double acc = 0.0;
+  // row loops run four rows per trip (loads of all four first): with one row per trip every trip waited for its
+  // own memory round trip; the summation order is that of the plain loop
+  const int64_t st = (int64_t)RG * k;                       // element stride between a thread's consecutive rows
   if (on) {
     const double* W0 = a.W[0];
-    for (int64_t i = r0 + rr; i < r1; i += RG) acc = fma(w[i * k + c], __ldg(W0 + i * k + c), acc);
+    int64_t e = (r0 + rr) * k + c;
+    const int64_t eend = r1 * k;
+    for (; e + 3 * st < eend; e += 4 * st) {
+      const double w0 = w[e], w1 = w[e + st], w2 = w[e + 2 * st], w3 = w[e + 3 * st];
+      const double x0 = __ldg(W0 + e), x1 = __ldg(W0 + e + st), x2 = __ldg(W0 + e + 2 * st), x3 = __ldg(W0 + e + 3 * st);
+      acc = fma(w0, x0, acc); acc = fma(w1, x1, acc); acc = fma(w2, x2, acc); acc = fma(w3, x3, acc);
+    }
+    for (; e < eend; e += st) acc = fma(w[e], __ldg(W0 + e), acc);
   }
   for (int t = 0; t < j; ++t) {
     red[threadIdx.x] = on ? acc : 0.0;
@@ -605,19 +616,30 @@ mgs_sweep_kernel(int64_t n, int k, int j, MgsArgs a, double* __restrict__ w, dou
     if (on) {
       const double h = hs[c];
       const double* Wt = a.W[t];
+      int64_t e = (r0 + rr) * k + c;
+      const int64_t eend = r1 * k;
       if (t + 1 < j) {
         const double* Wn = a.W[t + 1];
-        for (int64_t i = r0 + rr; i < r1; i += RG) {
-          const int64_t e = i * k + c;
+        for (; e + 3 * st < eend; e += 4 * st) {
+          const double t0 = __ldg(Wt + e), t1 = __ldg(Wt + e + st), t2 = __ldg(Wt + e + 2 * st), t3 = __ldg(Wt + e + 3 * st);
+          const double w0 = w[e], w1 = w[e + st], w2 = w[e + 2 * st], w3 = w[e + 3 * st];
+          const double n0 = __ldg(Wn + e), n1 = __ldg(Wn + e + st), n2 = __ldg(Wn + e + 2 * st), n3 = __ldg(Wn + e + 3 * st);
+          const double v0 = fma(-h, t0, w0), v1 = fma(-h, t1, w1), v2 = fma(-h, t2, w2), v3 = fma(-h, t3, w3);
+          w[e] = v0; w[e + st] = v1; w[e + 2 * st] = v2; w[e + 3 * st] = v3;
+          acc = fma(v0, n0, acc); acc = fma(v1, n1, acc); acc = fma(v2, n2, acc); acc = fma(v3, n3, acc);
+        }
+        for (; e < eend; e += st) {
           const double v = fma(-h, __ldg(Wt + e), w[e]);
           w[e] = v;
           acc = fma(v, __ldg(Wn + e), acc);
         }
       } else {
-        for (int64_t i = r0 + rr; i < r1; i += RG) {
-          const int64_t e = i * k + c;
-          w[e] = fma(-h, __ldg(Wt + e), w[e]);
+        for (; e + 3 * st < eend; e += 4 * st) {
+          const double t0 = __ldg(Wt + e), t1 = __ldg(Wt + e + st), t2 = __ldg(Wt + e + 2 * st), t3 = __ldg(Wt + e + 3 * st);
+          const double w0 = w[e], w1 = w[e + st], w2 = w[e + 2 * st], w3 = w[e + 3 * st];
+          w[e] = fma(-h, t0, w0); w[e + st] = fma(-h, t1, w1); w[e + 2 * st] = fma(-h, t2, w2); w[e + 3 * st] = fma(-h, t3, w3);
         }
+        for (; e < eend; e += st) w[e] = fma(-h, __ldg(Wt + e), w[e]);
       }
     }
   }
@@ -625,29 +647,48 @@ mgs_sweep_kernel(int64_t n, int k, int j, MgsArgs a, double* __restrict__ w, dou
 
 static unsigned long long* g_mgs_ctr = nullptr;
 static unsigned long long g_mgs_base = 0;
-static int g_mgs_dev = -1, g_mgs_max_grid = 0;
+static int g_mgs_dev = -1;
 
-extern "C" int eigd_mgs_sweep(int64_t n, int k, int j, const double* const* W, double* const* H, double* d_w,
-                              double* d_work) {
-  if (n <= 0 || j <= 0) return 0;
-  if (k < 1 || k > MGS_KMAX) { eigd_set_error("mgs_sweep: k = %d outside 1..%d", k, MGS_KMAX); return 7; }
+// the monotonic arrival counter of the cooperative kernels of this file (stream-ordered launches: every launch adds
+// exactly barriers x grid arrivals, so the next launch starts from a known base)
+static int coop_counter_ready() {
   int dev = 0;
   EIGD_CUDA(cudaGetDevice(&dev));
   if (dev != g_mgs_dev) {
-    int sms = 0, occ = 0;
-    EIGD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    EIGD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mgs_sweep_kernel, 256, 0));
-    if (occ < 1) { eigd_set_error("mgs_sweep: kernel does not fit on an SM"); return 7; }
-    g_mgs_max_grid = sms * (occ < 2 ? occ : 2);
-    if (g_mgs_max_grid > RED_MAX_CTAS) g_mgs_max_grid = RED_MAX_CTAS;
     EIGD_CUDA(cudaMalloc(&g_mgs_ctr, sizeof(unsigned long long)));
     EIGD_CUDA(cudaMemsetAsync(g_mgs_ctr, 0, sizeof(unsigned long long), g_eigd_stream));
     g_mgs_base = 0;
     g_mgs_dev = dev;
   }
+  return 0;
+}
+
+template <class Kernel>
+static int coop_max_grid(Kernel kernel, int per_sm, int cap, int* max_grid) {
+  if (*max_grid > 0) return 0;
+  int dev = 0, sms = 0, occ = 0;
+  EIGD_CUDA(cudaGetDevice(&dev));
+  EIGD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  EIGD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 256, 0));
+  if (occ < 1) { eigd_set_error("cooperative kernel does not fit on an SM"); return 7; }
+  int g = sms * (occ < per_sm ? occ : per_sm);
+  *max_grid = g > cap ? cap : g;
+  return 0;
+}
+
+extern "C" int eigd_mgs_sweep(int64_t n, int k, int j, const double* const* W, double* const* H, double* d_w,
+                              double* d_work) {
+  if (n <= 0 || j <= 0) return 0;
+  if (k < 1 || k > MGS_KMAX) { eigd_set_error("mgs_sweep: k = %d outside 1..%d", k, MGS_KMAX); return 7; }
+  static int max_grid = 0, per_sm = -1;
+  if (per_sm < 0) { const char* e = getenv("EIGD_MGS_CTAS_PER_SM"); per_sm = e ? atoi(e) : 4; if (per_sm < 1) per_sm = 1; }   // developer tuning; measured at C2, 8 blocks: 146 / 130 / 125 us with 2 / 3 / 4
+  int rc;
+  // the two halves of the partial-sum buffer (2 x grid x k doubles) live in the reduction workspace
+  const int cap = (int)(eigd_gemm_tn_workspace(TN_KMAX, TN_KMAX) / (2 * MGS_KMAX));
+  if ((rc = coop_counter_ready()) || (rc = coop_max_grid(mgs_sweep_kernel, per_sm, cap, &max_grid))) return rc;
   const int RG = 256 / k;
   int64_t want = (n + (int64_t)RG * 4 - 1) / ((int64_t)RG * 4);
-  int grid = (int)(want < 1 ? 1 : (want > g_mgs_max_grid ? g_mgs_max_grid : want));
+  int grid = (int)(want < 1 ? 1 : (want > max_grid ? max_grid : want));
   for (int j0 = 0; j0 < j; j0 += MGS_MAX) {
     const int jj = j - j0 < MGS_MAX ? j - j0 : MGS_MAX;
     MgsArgs a;

@@ -29,7 +29,23 @@ spmv_kernel(int n, const int* __restrict__ indptr, const int* __restrict__ indic
     int p0 = 0, p1 = 0;
     if (valid) { p0 = indptr[row]; p1 = indptr[row + 1]; }
     double acc = 0.0;
-    for (int p = p0 + lane; p < p1; p += G) acc = fma(vals[p], X[(int64_t)indices[p] * xrs], acc);
+    // three entries per lane and trip: all index / value loads first, then the three gathers, then the products
+    // (same summation order as a plain loop; two memory round trips per trip instead of six)
+    for (int p = p0 + lane; p < p1; p += 3 * G) {
+      const bool b1 = p + G < p1, b2 = p + 2 * G < p1;
+      const int i0 = indices[p];
+      const int i1 = b1 ? indices[p + G] : 0;
+      const int i2 = b2 ? indices[p + 2 * G] : 0;
+      const double v0 = vals[p];
+      const double v1 = b1 ? vals[p + G] : 0.0;
+      const double v2 = b2 ? vals[p + 2 * G] : 0.0;
+      const double x0 = X[(int64_t)i0 * xrs];
+      const double x1 = b1 ? X[(int64_t)i1 * xrs] : 0.0;
+      const double x2 = b2 ? X[(int64_t)i2 * xrs] : 0.0;
+      acc = fma(v0, x0, acc);
+      if (b1) acc = fma(v1, x1, acc);
+      if (b2) acc = fma(v2, x2, acc);
+    }
 #pragma unroll
     for (int o = G >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o, G);
     if (valid && lane == 0) {
@@ -50,9 +66,24 @@ spmm_kernel(int n, const int* __restrict__ indptr, const int* __restrict__ indic
   for (int64_t row = gid; row < n; row += ngroups) {
     int p0 = indptr[row], p1 = indptr[row + 1];
     double acc = 0.0;
+    // four entries per trip: the (broadcast) index / value loads first, then the four gathers, then the products in
+    // the order of the plain loop (one entry per trip, each with its own index -> value chain, is latency bound)
     if (lane < k) {
-      for (int p = p0; p < p1; ++p)
-        acc = fma(vals[p], X[(int64_t)indices[p] * xrs + (int64_t)lane * xcs], acc);
+      const int64_t xoff = (int64_t)lane * xcs;
+      int p = p0;
+      for (; p + 4 <= p1; p += 4) {
+        const int i0 = indices[p], i1 = indices[p + 1], i2 = indices[p + 2], i3 = indices[p + 3];
+        const double v0 = vals[p], v1 = vals[p + 1], v2 = vals[p + 2], v3 = vals[p + 3];
+        const double x0 = X[(int64_t)i0 * xrs + xoff], x1 = X[(int64_t)i1 * xrs + xoff];
+        const double x2 = X[(int64_t)i2 * xrs + xoff], x3 = X[(int64_t)i3 * xrs + xoff];
+        acc = fma(v0, x0, acc);
+        acc = fma(v1, x1, acc);
+        acc = fma(v2, x2, acc);
+        acc = fma(v3, x3, acc);
+      }
+      for (; p < p1; ++p) acc = fma(vals[p], X[(int64_t)indices[p] * xrs + xoff], acc);
+    }
+    if (lane < k) {
       int64_t yi = row * yrs + (int64_t)lane * ycs;
       double y0 = (beta == 0.0) ? 0.0 : beta * Y[yi];
       Y[yi] = fma(alpha, acc, y0);

@@ -408,7 +408,9 @@ def copy2d(src, dst):
 
 
 def project(U, V, X):
-    """Oblique projection X <- X - U (V^T X)   (reference _project, eigenvector_derivatives.py:26-30)"""
+    """Oblique projection X <- X - U (V^T X)   (reference _project, eigenvector_derivatives.py:26-30).
+    (A single cooperative launch for the whole projection was measured slower than these two products -- 68 vs
+    52 us at C2 -- and removed; profiles/r1_sibk_step_kernels_ab.txt.)"""
     t = gemm_tn(V, X)
     gemm_nn(U, t, X, alpha=-1.0, beta=1.0)
     return X

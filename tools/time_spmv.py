@@ -19,4 +19,15 @@ for kind, nx in (("thermal", 500), ("plane_stress", 352)):
         e0.record(); M.spmm(x, out=y); e1.record(); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
     by = K.nnz * 12 + K.shape[0] * 20
-    print("%s n=%d nnz=%d  G=%s  %.1f us  %.0f GB/s" % (kind, K.shape[0], K.nnz, os.environ.get("EIGD_SPMV_G", "8"), min(ts) * 1e3, by / min(ts) / 1e6))
+    print("%s n=%d nnz=%d  G=%s  %.1f us  %.0f GB/s" % (kind, K.shape[0], K.nnz, os.environ.get("EIGD_SPMV_G", "4"), min(ts) * 1e3, by / min(ts) / 1e6))
+    for k in (2, 10, 20):
+        xk = torch.randn(K.shape[0], k, dtype=torch.float64, device="cuda")
+        yk = torch.empty_like(xk)
+        ts = []
+        for it in range(10):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); M.spmm(xk, out=yk); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        by = K.nnz * 12 + K.shape[0] * (4 + 16 * k)
+        print("   spmm k=%d  %.1f us  %.0f GB/s" % (k, min(ts) * 1e3, by / min(ts) / 1e6))
