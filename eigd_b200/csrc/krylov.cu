@@ -13,6 +13,8 @@
 
 int eigd_basis_dots(int64_t n, int j, const double* V, int64_t ldv, const double* w, double* out, double* work);
 int eigd_basis_axpy(int64_t n, int j, const double* V, int64_t ldv, const double* S, int lds, double alpha, double* w);
+int eigd_csr_spmv_dot(int n, const int* indptr, const int* indices, const double* vals, const double* x, double* y,
+                      double* out, double* work);
 
 namespace {
 
@@ -73,8 +75,12 @@ extern "C" int eigd_lanczos_extend(eigd_factor* f, int refine, int n, const int*
     if ((rc = eigd_basis_axpy(n, j + 1, d_V, ld, d_g, 1, -1.0, d_w))) return rc;
     // B-norm of the new direction and the next basis vector
     double* bvn = d_BV + (int64_t)(j + 1) * ld;
-    if ((rc = eigd_csr_spmm(n, d_b_indptr, d_b_indices, d_b_vals, d_w, 1, 1, bvn, 1, 1, 1, 1.0, 0.0))) return rc;
-    if ((rc = eigd_basis_dots(n, 1, bvn, ld, d_w, d_ab + ldab + j, d_work))) return rc;
+    if ((int64_t)(n + 63) / 64 <= eigd_gemm_tn_workspace(32, 32)) {
+      if ((rc = eigd_csr_spmv_dot(n, d_b_indptr, d_b_indices, d_b_vals, d_w, bvn, d_ab + ldab + j, d_work))) return rc;
+    } else {
+      if ((rc = eigd_csr_spmm(n, d_b_indptr, d_b_indices, d_b_vals, d_w, 1, 1, bvn, 1, 1, 1, 1.0, 0.0))) return rc;
+      if ((rc = eigd_basis_dots(n, 1, bvn, ld, d_w, d_ab + ldab + j, d_work))) return rc;
+    }
     EIGD_LAUNCH(lanczos_finish_kernel, ew_grid(n), 256, 0, (int64_t)n, d_w, d_ab + ldab + j, d_V + (int64_t)(j + 1) * ld, bvn,
                 d_h + j, d_g + j, d_ab + j);
     EIGD_CHECK_LAUNCH();

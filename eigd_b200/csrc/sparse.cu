@@ -91,6 +91,71 @@ spmm_kernel(int n, const int* __restrict__ indptr, const int* __restrict__ indic
   }
 }
 
+// y = A x and, in the same launch, dot = sum_i y_i x_i (the B-norm of a new Lanczos direction: one launch instead of
+// an SpMV, a one-row dot kernel and its reduction).  One row per group of G lanes, no row loop; block sums go to
+// partial[cta], the last CTA to finish (ticket) adds them in a fixed order -> bitwise reproducible.
+__device__ unsigned int g_spmv_ticket = 0;
+
+template <int G>
+__global__ void __launch_bounds__(256)
+spmv_dot_kernel(int n, const int* __restrict__ indptr, const int* __restrict__ indices, const double* __restrict__ vals,
+                const double* __restrict__ X, double* __restrict__ Y, double* __restrict__ partial,
+                double* __restrict__ out, unsigned int* __restrict__ ticket) {
+  constexpr int GPB = 256 / G;                              // groups (rows) per CTA
+  __shared__ double red[256];
+  __shared__ bool last;
+  const int tid = threadIdx.x, lane = tid & (G - 1), grp = tid / G;
+  const int64_t row = (int64_t)blockIdx.x * GPB + grp;
+  const bool valid = row < n;
+  int p0 = 0, p1 = 0;
+  if (valid) { p0 = indptr[row]; p1 = indptr[row + 1]; }
+  double acc = 0.0;
+  for (int p = p0 + lane; p < p1; p += 3 * G) {             // same batching and summation order as spmv_kernel
+    const bool b1 = p + G < p1, b2 = p + 2 * G < p1;
+    const int i0 = indices[p];
+    const int i1 = b1 ? indices[p + G] : 0;
+    const int i2 = b2 ? indices[p + 2 * G] : 0;
+    const double v0 = vals[p];
+    const double v1 = b1 ? vals[p + G] : 0.0;
+    const double v2 = b2 ? vals[p + 2 * G] : 0.0;
+    const double x0 = X[i0];
+    const double x1 = b1 ? X[i1] : 0.0;
+    const double x2 = b2 ? X[i2] : 0.0;
+    acc = fma(v0, x0, acc);
+    if (b1) acc = fma(v1, x1, acc);
+    if (b2) acc = fma(v2, x2, acc);
+  }
+#pragma unroll
+  for (int o = G >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o, G);
+  double t = 0.0;
+  if (valid && lane == 0) {
+    Y[row] = acc;
+    t = acc * X[row];
+  }
+  red[tid] = t;                                             // zero for every lane but the group leaders
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (tid < o) red[tid] += red[tid + o];
+    __syncthreads();
+  }
+  if (tid == 0) partial[blockIdx.x] = red[0];
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  double s = 0.0;
+  for (int c = tid; c < (int)gridDim.x; c += 256) s += __ldcg(partial + c);
+  red[tid] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (tid < o) red[tid] += red[tid + o];
+    __syncthreads();
+  }
+  if (tid == 0) { out[0] = red[0]; *ticket = 0u; }
+}
+
 inline int grid_for(int64_t groups_needed, int groups_per_block) {
   int64_t g = (groups_needed + groups_per_block - 1) / groups_per_block;
   int64_t cap = 148 * 32;
@@ -98,6 +163,18 @@ inline int grid_for(int64_t groups_needed, int groups_per_block) {
 }
 
 }  // namespace
+
+// internal (krylov.cu): y = A x, out[0] = y . x; work must hold ceil(n / 64) doubles
+int eigd_csr_spmv_dot(int n, const int* indptr, const int* indices, const double* vals, const double* x, double* y,
+                      double* out, double* work) {
+  if (n <= 0) return 0;
+  unsigned int* ticket = nullptr;
+  EIGD_CUDA(cudaGetSymbolAddress((void**)&ticket, g_spmv_ticket));
+  const int grid = (n + 63) / 64;
+  EIGD_LAUNCH(spmv_dot_kernel<4>, grid, 256, 0, n, indptr, indices, vals, x, y, work, out, ticket);
+  EIGD_CHECK_LAUNCH();
+  return 0;
+}
 
 extern "C" int eigd_csr_spmm(int n, const int* indptr, const int* indices, const double* vals, const double* X,
                              int64_t xrs, int64_t xcs, double* Y, int64_t yrs, int64_t ycs, int k, double alpha,
