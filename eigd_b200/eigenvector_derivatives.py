@@ -644,22 +644,29 @@ def _sibk_dev(Phib_d, Ad, Bd, lam, Phi_d, mode, psi_d, sigma, factor, rtol, atol
     n, N = Phib_d.shape
     lam = np.asarray(lam, dtype=float)
     lam_d = small_to_dev(lam)
-    if rnorm0 is None:                                                           # :1170 (max over ALL modes)
-        rnorm0 = float(np.sqrt(np.max(to_host(D.col_dot(Phib_d, Phib_d)))))
+    # Everything up to the first Krylov vector is queued before the first read-back, so the device runs through the
+    # set-up once instead of draining at four small device -> host copies (the second projection and its norms are
+    # wasted only when every mode is already converged).
+    rn_d = D.col_dot(Phib_d, Phib_d) if rnorm0 is None else None                 # :1170 (max over ALL modes)
     BPhi = Bd.spmm(Phi_d)                                                        # :1173
-    G = -to_host(D.gemm_tn(Phi_d, Phib_d))                                       # :1180
+    G_d = D.gemm_tn(Phi_d, Phib_d)                                               # :1180
     R = _neg_sum(_contig(Phib_d), _apply_L(Ad, Bd, lam_d, psi_d, mode))          # :1189-1193
     _project(BPhi, Phi_d, R)
-    beta0 = _col_norms(R)
+    beta0_d = D.col_dot(R, R)
+    # first Krylov vector: w0 = P R / ||P R||   (:1227-1234 with bs = 1)
+    W = [R]
+    _project(BPhi, Phi_d, W[0])
+    r0_d = D.col_dot(W[0], W[0])
+    if rn_d is not None:
+        rnorm0 = float(np.sqrt(np.max(to_host(rn_d))))
+    G = -to_host(G_d)
+    beta0 = np.sqrt(to_host(beta0_d))
     hist = [[b] for b in beta0]
     active = ~((beta0 < rtol * rnorm0) | (beta0 < atol))
     info = [0] * N
     if not active.any():
         return G, info, hist
-    # first Krylov vector: w0 = P R / ||P R||   (:1227-1234 with bs = 1)
-    W = [R]
-    _project(BPhi, Phi_d, W[0])
-    r0 = _col_norms(W[0])
+    r0 = np.sqrt(to_host(r0_d))
     D.col_scale(W[0], small_to_dev(_masked_inverse(r0, active)), mode=0)
     Z = []
     alpha = (lam - sigma) if mode == "normal" else -(lam - sigma)                 # :1262-1266
