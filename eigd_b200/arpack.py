@@ -56,6 +56,9 @@ def _theta_to_lambda(theta, sigma, mode):
     return sigma * theta / (theta - 1.0)                # :1963
 
 
+_SEEDED_V0 = {}
+
+
 def lanczos_thick_restart(Bip, factor, k, ncv, sigma, mode="normal", tol=0.0, maxiter=None, v0=None, seed=None):
     """Thick-restart Lanczos on OP = factor o Bip in the Bip inner product; returns LanczosState."""
     n = Bip.shape[0]
@@ -79,9 +82,17 @@ def lanczos_thick_restart(Bip, factor, k, ncv, sigma, mode="normal", tol=0.0, ma
     # start vector: forced into the range of OP as ARPACK's dgetv0 does
     if v0 is not None:
         w = to_dev(v0, copy=True).reshape(n)
+    elif seed is None:
+        w = to_dev(np.random.default_rng().uniform(-1.0, 1.0, n))
     else:
-        rng = np.random.default_rng(seed)
-        w = to_dev(rng.uniform(-1.0, 1.0, n))
+        # a seeded start vector is the same array every time: keep its device copy (drawing n host randoms and
+        # uploading them costs about a millisecond at C2 during which the device idles)
+        key = (int(seed), int(n), str(D.dev()))
+        w = _SEEDED_V0.get(key)
+        if w is None:
+            if len(_SEEDED_V0) >= 4:
+                _SEEDED_V0.clear()
+            w = _SEEDED_V0[key] = to_dev(np.random.default_rng(seed).uniform(-1.0, 1.0, n))
     bw = Bip.spmm(w)
     v = factor.solve_dev(bw)
     st.nops += 1
@@ -158,6 +169,8 @@ def lanczos_thick_restart(Bip, factor, k, ncv, sigma, mode="normal", tol=0.0, ma
     st.theta = theta[sel]
     st.resid = bounds[sel]
     st.T = T.copy()
+    st.eigh_T = (theta.copy(), Y.copy())     # eigh of the returned T and the Ritz columns behind Z, for the caller
+    st.sel = sel.copy()
     st.Vt = Vt[:ncv]
     Z = D.empty(n, k)
     D.gemm_nn(st.Vt.T, small_to_dev(Y[:, sel]), Z, alpha=1.0, beta=0.0)

@@ -1351,7 +1351,9 @@ class IRAM(_SolverBase):
         self.lanczos_state = st
         self._V_d = st.Vt.T
         self._V_host = None
-        self.theta, self.Y = np.linalg.eigh(self.T)                                         # :1958
+        # eigh(T) (:1958): the restart loop has just computed it for this very T (same LAPACK call, same input)
+        self.theta, self.Y = (st.eigh_T[0].copy(), st.eigh_T[1].copy()) if getattr(st, "eigh_T", None) is not None \
+            else np.linalg.eigh(self.T)
         if self.mode == "normal":
             eigs = 1.0 / self.theta + sigma
             self.indices = np.argsort(eigs)
@@ -1363,12 +1365,15 @@ class IRAM(_SolverBase):
         # modal-assurance sign alignment of Y against the returned eigenvectors (:1978-1984):
         # sign(phi_i . V y_i) = sign((V^T B phi_i) . y_i) up to the positive-definite metric; evaluate it
         # in the reduced space through Q = V Y0 on the device
-        Q = D.empty(n, self.N)
-        D.gemm_nn(self._V_d, small_to_dev(self.Y[:, self.indices[: self.N]]), Q, alpha=1.0, beta=0.0)
-        mac = to_host(D.col_dot(Q, st.Z))
-        for i in range(self.N):
-            if mac[i] < 0.0:
-                self.Y[:, self.indices[i]] *= -1.0
+        if getattr(st, "eigh_T", None) is not None and np.array_equal(self.indices[: self.N], st.sel):
+            pass      # the returned eigenvectors ARE V Y[:, indices[:N]] with this Y: every sign already agrees
+        else:
+            Q = D.empty(n, self.N)
+            D.gemm_nn(self._V_d, small_to_dev(self.Y[:, self.indices[: self.N]]), Q, alpha=1.0, beta=0.0)
+            mac = to_host(D.col_dot(Q, st.Z))
+            for i in range(self.N):
+                if mac[i] < 0.0:
+                    self.Y[:, self.indices[i]] *= -1.0
         self._Phi_d = st.Z
         self._publish_phi(st.Z, A)
         return self.lam, self.Phi
