@@ -10,6 +10,7 @@ import ctypes
 import hashlib
 import time
 import warnings
+import weakref
 
 import numpy as np
 
@@ -514,6 +515,12 @@ class PatternCache:
         return (len(indptr), len(indices), int(indptr[::61].sum()), int(indices[::127].sum()),
                 int(indices[: 64].sum()), int(indices[-64:].sum()))
 
+    @staticmethod
+    def _refs(indptr, indices):
+        # weak references: the cache must not keep the caller's index arrays alive (a dead reference never matches,
+        # so a recycled id() cannot be mistaken for the old array)
+        return (weakref.ref(indptr), weakref.ref(indices))
+
     @classmethod
     def get(cls, indptr, indices):
         """-> (entry id, device indptr, device indices, fresh); arrays must be int32, contiguous, sorted rows.
@@ -525,17 +532,16 @@ class PatternCache:
         fp = cls._fingerprint(indptr, indices)
         for ent in cls._entries.get(fp, []):
             seen = ent[5]
-            if any(a is indptr and b is indices for a, b in seen):
+            if any(a() is indptr and b() is indices for a, b in seen):
                 return ent[0], ent[3], ent[4], False
             if np.array_equal(ent[1], indptr) and np.array_equal(ent[2], indices):
-                if len(seen) >= 8:
-                    del seen[0]
-                seen.append((indptr, indices))
+                seen[:] = [(a, b) for a, b in seen if a() is not None and b() is not None][-7:]
+                seen.append(cls._refs(indptr, indices))
                 return ent[0], ent[3], ent[4], False
         if sum(len(v) for v in cls._entries.values()) > 16:
             cls._entries.clear()
         eid = "p%d_%d_%d" % (fp[0], fp[1], id(indices))
-        ent = (eid, indptr.copy(), indices.copy(), h2d(indptr), h2d(indices), [(indptr, indices)])
+        ent = (eid, indptr.copy(), indices.copy(), h2d(indptr), h2d(indices), [cls._refs(indptr, indices)])
         cls._entries.setdefault(fp, []).append(ent)
         return eid, ent[3], ent[4], True
 
