@@ -10,7 +10,6 @@ import ctypes
 import hashlib
 import time
 import warnings
-import weakref
 
 import numpy as np
 
@@ -30,6 +29,7 @@ class _State:
     device = None
     work = None
     ready = False
+    stream = None      # cudaStream_t the native library is currently bound to
 
 
 def _ptr(t):
@@ -86,17 +86,31 @@ def init(device=None):
         return device
     torch.cuda.set_device(device)
     _State.device = device
+    _State.stream = None
     nwork = lib.eigd_gemm_tn_workspace(32, 32)
     _State.work = torch.empty(int(nwork), dtype=F64, device=device)
-    # run on torch's current stream so torch.cuda.Event timing and torch ops order with us
-    check(lib.eigd_set_stream(ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)), "set_stream")
     _State.ready = True
+    _bind_stream()
     return device
 
 
+def _bind_stream():
+    """The native kernels launch on the stream bound with eigd_set_stream; the torch ops interleaved with them
+    (copies, clones, event records, NCCL) follow torch's CURRENT stream.  Re-bind whenever the two differ, so that a
+    caller working under ``torch.cuda.stream(s)`` gets one consistent order instead of a race."""
+    cur = torch.cuda.current_stream(_State.device).cuda_stream
+    if cur != _State.stream:
+        check(_lib.load().eigd_set_stream(ctypes.c_void_p(cur)), "set_stream")
+        _State.stream = cur
+
+
 def dev():
+    """The selected device; every device-side helper of the package passes through here (or through ``empty`` /
+    ``zeros`` / ``to_device``) before it launches, which keeps the native stream bound to torch's current one."""
     if not _State.ready:
         init()
+    else:
+        _bind_stream()
     return _State.device
 
 
@@ -506,42 +520,30 @@ class PatternCache:
 
     K, M and K - sigma*M of one design -- and of every later design on the same mesh -- have identical
     patterns (examples/natural_frequency.py:94-104,157,233), so the int32 structure is uploaded once and
-    only the fp64 values travel per matrix.  Look-up: a cheap fingerprint (sizes + strided sums) selects
-    the candidate, a full array comparison against the cached host copy confirms it."""
+    only the fp64 values travel per matrix.  Look-up: a cheap fingerprint (sizes + strided sums) selects the
+    candidates, a FULL comparison against the cached host copy confirms the hit -- always: a sampled fingerprint
+    or the identity of the caller's array objects proves nothing about arrays that may have been edited in place.
+    Entry ids come from a counter (never from ``id()``: CPython recycles addresses of dead arrays)."""
     _entries = {}
+    _next_id = 0
 
     @staticmethod
     def _fingerprint(indptr, indices):
         return (len(indptr), len(indices), int(indptr[::61].sum()), int(indices[::127].sum()),
                 int(indices[: 64].sum()), int(indices[-64:].sum()))
 
-    @staticmethod
-    def _refs(indptr, indices):
-        # weak references: the cache must not keep the caller's index arrays alive (a dead reference never matches,
-        # so a recycled id() cannot be mistaken for the old array)
-        return (weakref.ref(indptr), weakref.ref(indices))
-
     @classmethod
     def get(cls, indptr, indices):
-        """-> (entry id, device indptr, device indices, fresh); arrays must be int32, contiguous, sorted rows.
-
-        The full comparison costs a pass over both arrays (3 ms per gradient at C2 for K, M and K - sigma*M), so
-        an entry also remembers the array *objects* it was last confirmed against: the same objects with an
-        unchanged fingerprint are accepted without the pass (index arrays of an assembled FE matrix are not edited
-        in place; scipy operations return new arrays, which take the full comparison)."""
+        """-> (entry id, device indptr, device indices, fresh); arrays must be int32, contiguous, sorted rows."""
         fp = cls._fingerprint(indptr, indices)
         for ent in cls._entries.get(fp, []):
-            seen = ent[5]
-            if any(a() is indptr and b() is indices for a, b in seen):
-                return ent[0], ent[3], ent[4], False
             if np.array_equal(ent[1], indptr) and np.array_equal(ent[2], indices):
-                seen[:] = [(a, b) for a, b in seen if a() is not None and b() is not None][-7:]
-                seen.append(cls._refs(indptr, indices))
                 return ent[0], ent[3], ent[4], False
         if sum(len(v) for v in cls._entries.values()) > 16:
             cls._entries.clear()
-        eid = "p%d_%d_%d" % (fp[0], fp[1], id(indices))
-        ent = (eid, indptr.copy(), indices.copy(), h2d(indptr), h2d(indices), [cls._refs(indptr, indices)])
+        cls._next_id += 1
+        eid = "p%d" % cls._next_id
+        ent = (eid, indptr.copy(), indices.copy(), h2d(indptr), h2d(indices))
         cls._entries.setdefault(fp, []).append(ent)
         return eid, ent[3], ent[4], True
 

@@ -17,7 +17,6 @@ Structural differences from the reference (results are the same):
   * ``IRAM`` uses the thick-restart Lanczos of ``eigd_b200.arpack`` (see there).
 """
 import warnings
-import weakref
 
 import numpy as np
 import torch
@@ -36,6 +35,35 @@ def _is_complex_host(M):
     """scipy sparse matrix with complex values (a complex-step operand); device matrices are always real"""
     d = getattr(M, "data", None)
     return isinstance(d, np.ndarray) and np.iscomplexobj(d)
+
+
+def _check_symmetric_sampled(mat, nsample=64):
+    """The reference's ``splu`` takes any square matrix; the LDL^T here needs a symmetric one, and a CSC operand is
+    read as the CSR arrays of its transpose.  A full symmetry test costs more than the factorisation's upload, so
+    compare ``nsample`` rows / columns entry by entry (structure and values) and refuse anything else."""
+    if mat.format not in ("csr", "csc") or mat.shape[0] != mat.shape[1] or mat.nnz == 0:
+        return
+    n = mat.shape[0]
+    if not mat.has_sorted_indices:
+        mat.sort_indices()
+    ptr, idx, val = mat.indptr, mat.indices, mat.data
+    major = np.unique(np.linspace(0, n - 1, min(nsample, n)).astype(np.int64))
+    cnt = np.minimum(ptr[major + 1] - ptr[major], 16).astype(np.int64)
+    j = np.repeat(major, cnt)                                           # sampled entries (i, j) of the compressed axis
+    pos = np.repeat(ptr[major].astype(np.int64) - np.concatenate([[0], np.cumsum(cnt)[:-1]]), cnt) + np.arange(int(cnt.sum()))
+    i, v = idx[pos].astype(np.int64), val[pos]
+    lo, hi = ptr[i].astype(np.int64), ptr[i + 1].astype(np.int64)        # vectorised bisection for j in segment i
+    for _ in range(int(np.ceil(np.log2(max(int((hi - lo).max()), 2)))) + 1):
+        mid = (lo + hi) // 2
+        less = (mid < hi) & (idx[np.minimum(mid, len(idx) - 1)] < j)
+        lo, hi = np.where(less, mid + 1, lo), np.where(less, hi, mid)
+    q = np.minimum(lo, len(idx) - 1)
+    scale = float(np.abs(v).max()) or 1.0
+    bad = (lo >= ptr[i + 1]) | (idx[q] != j) | (np.abs(val[q] - v) > 1e-10 * scale)
+    if bad.any():
+        k = int(np.argmax(bad))
+        raise ValueError("SpLuOperator: the matrix is not symmetric (entry (%d, %d)); the GPU factorisation is an "
+                         "LDL^T of a symmetric shifted matrix" % (i[k], j[k]))
 
 
 def _check_mode(mode):
@@ -74,6 +102,7 @@ class SpLuOperator:
                 csr, self.tangent = dual.split_csr(mat, symmetric=True)
                 XFER["h2d"] += 2 * csr.uploaded_bytes
             else:
+                _check_symmetric_sampled(mat)
                 csr = D.CsrDevice.from_scipy(mat, symmetric=True)   # symmetric: CSC arrays of mat are CSR arrays of mat
                 XFER["h2d"] += csr.uploaded_bytes
         if csr.shape[0] != csr.shape[1]:
@@ -105,7 +134,7 @@ class SpLuOperator:
         self.info = self.lu.info()
         if self.info["non_finite"]:
             raise RuntimeError("SpLuOperator: non-finite pivots in the LDL^T factorisation (singular shifted matrix?)")
-        self.probe = None
+        self.probe = self.probe_refined = None
         if refine is None:
             if self.info["perturbed_pivots"]:
                 refine = 1
@@ -120,14 +149,33 @@ class SpLuOperator:
             else:
                 refine = 0
         self.refine = int(refine)
+        if self.refine and (self.info["perturbed_pivots"] or self.info["negative_pivots"]):
+            # static pivoting is only as good as the refined solve it leaves behind: measure that, iterate the
+            # refinement to tolerance if one step is not enough, and say so loudly if it cannot be reached
+            # (a shift that sits on an eigenvalue; the reference's partially pivoted LU would lose accuracy there too)
+            self.probe_refined = self._probe_residual(refined=True)
+            while self.probe_refined > 1e-10 and self.refine < 4:
+                self.refine += 1
+                self.probe_refined = self._probe_residual(refined=True)
+            if not self.probe_refined <= 1e-8:
+                warnings.warn("SpLuOperator: the LDL^T factorisation of the shifted matrix is inaccurate (relative residual "
+                              "%.1e after %d refinement steps, %d perturbed and %d negative pivots); move the shift away "
+                              "from the spectrum" % (self.probe_refined, self.refine, self.info["perturbed_pivots"],
+                                                     self.info["negative_pivots"]))
 
-    def _probe_residual(self):
-        """max |b - mat x| / max |b| of one unrefined solve with a fixed pseudo-random right-hand side."""
+    def _probe_residual(self, refined=False):
+        """max |b - mat x| / max |b| of one solve (plain LDL^T sweep, or the refined solve every caller gets) with a
+        fixed pseudo-random right-hand side."""
         n = self.shape[0]
         g = torch.Generator(device=D.dev())
         g.manual_seed(12345)
         b = torch.rand(n, dtype=D.F64, device=D.dev(), generator=g) - 0.5
-        x = self.lu.solve(b)
+        if refined:
+            c0 = self.count
+            x = self.solve_dev(b)
+            self.count = c0
+        else:
+            x = self.lu.solve(b)
         r = self.mat.spmm(x)
         D.axpby(1.0, b, -1.0, r, out=r)
         return float((r.abs().max() / b.abs().max()).item())
@@ -1036,47 +1084,23 @@ class _SolverBase:
         in device matrices keep them in HBM."""
         if isinstance(A, D.CsrDevice):
             self.Phi = Phi_d
-            self._Phi_host_sig = None
         else:
             self.Phi = to_host(Phi_d)
-            self._Phi_host_sig = self._signature(self.Phi)
 
     def _phi_dev(self):
-        """Device copy of the eigenvectors; the host array is authoritative if the caller has
-        modified it since solve() (the examples flip signs in place, natural_frequency.py:383-390)."""
+        """Device copy of the eigenvectors.  When ``solve`` returned a host array, that array is authoritative: the
+        callers slice it and edit it in place (sign flips, examples/natural_frequency.py:383-390), and nothing short
+        of reading all of it can tell whether they did -- so it is uploaded again at every entry point (20 MB at C2:
+        0.4 ms of DMA from the page-locked block ``solve`` returned it in).  No fingerprints, no reuse."""
         if is_dev(self.Phi):
             return self.Phi
-        if self._Phi_host_sig is not None and self._Phi_d is not None:
-            sig = self._signature(self.Phi)
-            if sig == self._Phi_host_sig:
-                return self._Phi_d
         self._Phi_d = to_dev(self.Phi)
-        self._Phi_host_sig = self._signature(self.Phi)
         return self._Phi_d
 
     def _phib_dev(self, Phib):
-        """Device copy of the adjoint right-hand sides.  ``solve_adjoint`` and ``add_total_derivative`` receive the
-        same host array (examples/natural_frequency.py:375-392); the copy uploaded for the first call is reused by
-        the second when it is the same array object with an unchanged signature (as for ``Phi`` above)."""
-        if is_dev(Phib):
-            return to_dev(Phib)
-        Phib = np.asarray(Phib)
-        if Phib.ndim != 2 or Phib.shape[0] == 0:
-            return to_dev(Phib)
-        last = getattr(self, "_Phib_last", None)
-        if last is not None and last[0]() is Phib and last[1] == self._signature(Phib):
-            return last[2]
-        Phib_d = to_dev(Phib)
-        try:
-            self._Phib_last = (weakref.ref(Phib), self._signature(Phib), Phib_d)
-        except TypeError:
-            self._Phib_last = None
-        return Phib_d
-
-    @staticmethod
-    def _signature(P):
-        # first row and column sums are enough to detect the sign flips / rescalings callers apply
-        return (P.shape, P[0].tobytes(), P[-1].tobytes(), float(P[:: max(1, P.shape[0] // 64)].sum()))
+        """Device copy of the adjoint right-hand sides: uploaded on every call (the caller owns the array and may
+        refill it between ``solve_adjoint`` and ``add_total_derivative``)."""
+        return to_dev(Phib)
 
     def _adjoint(self, lam, Phib, method, psi, rtol, atol, lanczos_guess, kwargs):
         n = self.A.shape[1]
@@ -1143,16 +1167,12 @@ class _SolverBase:
                 raise TypeError("unexpected keyword arguments %r" % sorted(kwargs))
         if shard is None:
             psi_d = psi_s
-        else:                                 # the two gathers of the sharded adjoint (dist.py)
+        elif method == "laa":
             psi_d = shard.allgather_cols(psi_s, N, transpose=D.copy2d)
-            if method != "laa":
-                parts = shard.allgather_object((G if G is not None else np.zeros((N, 0)), info, hist))
-                G = shard.merge_cols_host([p[0] for p in parts], N)
-                info_all, hist_all = [0] * N, [[] for _ in range(N)]
-                for r, p in enumerate(parts):
-                    for c, i in enumerate(shard.my_cols(N, r)):
-                        info_all[i], hist_all[i] = p[1][c], p[2][c]
-                info, hist = info_all, hist_all
+        else:                                 # ONE packed all-gather: psi columns + per-mode scalars (dist.py)
+            packed = shard.pack_mode_scalars(N, G if G is not None else np.zeros((N, 0)), info, hist)
+            psi_d, extras = shard.allgather_cols(psi_s, N, transpose=D.copy2d, extra=packed)
+            G, info, hist = shard.unpack_mode_scalars(N, extras, info_type=bool if method == "pcpg" else int)
         if method == "laa":
             G = -to_host(D.gemm_tn(Phi_d, Phib_d))
         self.adjoint_info = info
@@ -1176,7 +1196,7 @@ class BasicLanczos(_SolverBase):
         self.N, self.m_max, self.tol, self.Ntarget = N, m, tol, Ntarget
         self.eig_atol, self.mode, self.ortho_type = eig_atol, mode, ortho_type
         self.m = m
-        self._Phi_d = self._Phi_host_sig = self._Phib_last = None
+        self._Phi_d = None
 
     def _solve_reduced_problem(self, alpha, beta, sigma, m):
         T = np.diag(alpha[:m]) + np.diag(beta[: m - 1], 1) + np.diag(beta[: m - 1], -1)     # :1416-1439
@@ -1332,7 +1352,7 @@ class IRAM(_SolverBase):
         _check_mode(mode)
         self.mode = mode
         self.seed = None          # start-vector seed (scipy >= 1.15 draws it at random; None keeps that)
-        self._Phi_d = self._Phi_host_sig = self._Phib_last = None
+        self._Phi_d = None
 
     def solve(self, A, B, factor, sigma):
         n = self._common_solve_checks(A, B, factor)

@@ -204,11 +204,59 @@ def make_thermal_model(nx=128, ny=128, Lx=1.0, Ly=1.0, rfact=4.0, **kwargs):
     return ThermalTopologyAnalysis(fltr, conn, X, **kwargs)
 
 
-def make_natural_frequency_model(nx=128, ny=64, Lx=2.0, Ly=1.0, rfact=4.0, **kwargs):
-    """examples/natural_frequency.py ``make_model`` (:850-990) without symmetry map / point masses."""
+def natural_frequency_design_map(nx, ny, rfact=4.0, Mx=3, My=3, ns=2):
+    """Design-variable map, node sets and element sets of examples/natural_frequency.py ``make_model`` (:896-954):
+    Mx x My patches of non-design material (dvmap = -1, the filter treats them as x = 1) and a four-fold mirror
+    symmetry of the remaining nodes.  Same visiting order as the reference, so the design-variable numbering is
+    bit-identical (checked against the reference's own ``fltr.dvmap`` in tests/test_fullsize_golden_gpu.py)."""
+    nodes = np.arange((nx + 1) * (ny + 1), dtype=np.int64).reshape(nx + 1, ny + 1)
+    dvmap = np.zeros((nx + 1, ny + 1), dtype=np.int64)
+    node_sets, element_sets = {}, {}
+    ns = max(int(ns * ny // 32), int(rfact // 2))
+    sx, sy = nx // (Mx - 1), ny // (My - 1)
+    for i in range(Mx):
+        for j in range(My):
+            if i < Mx // 2:
+                imin, imax = max(0, sx * i - ns + 1), min(nx, sx * i + ns + 1)
+            else:
+                lo, hi = max(0, sx * (Mx - i - 1) - ns + 1), min(nx, sx * (Mx - i - 1) + ns + 1)
+                imin, imax = max(0, nx - hi), min(nx, nx - lo)
+            if j < My // 2:
+                jmin, jmax = max(0, sy * j - ns), min(ny, sy * j + ns)
+            else:
+                lo, hi = max(0, sy * (My - j - 1) - ns), min(ny, sy * (My - j - 1) + ns)
+                jmin, jmax = max(0, ny - hi), min(ny, ny - lo)
+            ii, jj = np.meshgrid(np.arange(imin, imax), np.arange(jmin, jmax), indexing="ij")
+            name = "node[%d,%d]" % (i, j)
+            node_sets[name] = nodes[ii, jj].ravel()
+            element_sets[name] = (ii + nx * jj).ravel()
+            dvmap[imin:imax, jmin:jmax] = -1
+    index = 0
+    for i in range(nx // 2 + 1):
+        js = np.nonzero(dvmap[i, : ny // 2 + 1] >= 0)[0]         # ascending j, as the reference's inner loop (:945-951)
+        ids = index + np.arange(len(js))
+        for a in (i, nx - i):
+            dvmap[a, js] = ids
+            dvmap[a, ny - js] = ids
+        index += len(js)
+    return dvmap.ravel(), index, node_sets, element_sets
+
+
+def make_natural_frequency_model(nx=128, ny=64, Lx=1.0, Ly=1.0, rfact=4.0, N=10, Mx=3, My=3, ns=2, symmetry=True,
+                                 projection=False, b0=None, **kwargs):
+    """examples/natural_frequency.py ``make_model`` (:850-976), including its symmetric design-variable map and the
+    non-design patches (``symmetry=False``: one design variable per node)."""
     conn, X = fe.grid_mesh(nx, ny, Lx, Ly)
-    fltr = fe.NodeFilter(conn, X, r0=rfact * (Ly / ny))
-    return NaturalFrequencyAnalysis(fltr, conn, X, **kwargs)
+    if symmetry:
+        dvmap, ndv, node_sets, element_sets = natural_frequency_design_map(nx, ny, rfact, Mx, My, ns)
+        fltr = fe.NodeFilter(conn, X, r0=rfact * (Ly / ny), dvmap=dvmap, num_design_vars=ndv, projection=bool(projection),
+                             beta=b0)
+    else:
+        node_sets, element_sets = {}, {}
+        fltr = fe.NodeFilter(conn, X, r0=rfact * (Ly / ny), projection=bool(projection), beta=b0)
+    model = NaturalFrequencyAnalysis(fltr, conn, X, N=N, **kwargs)
+    model.node_sets, model.element_sets = node_sets, element_sets
+    return model
 
 
 # ------------------------------------------------------------------------------------------

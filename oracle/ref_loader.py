@@ -11,10 +11,14 @@ reference's ``eigd/eigenvector_derivatives.py`` verbatim from where it lies, wit
   * ``SpLuOperator.__init__`` wrapped so ``LinearOperator.__init__`` runs first;
   * a stub ``matplotlib`` so the examples import.
 
-It exists so that ``tests/golden/make_golden.py`` can run the real reference in the build
-container and freeze its outputs as fixtures.  ``/root/reference`` does not exist on the
-GPU box, and nothing in the product, ``bench.py`` or ``-m gpu`` tests imports this file.
+It exists so that ``tests/golden/make_golden*.py`` can run the real reference in the build container
+and freeze its outputs as fixtures, so that ``bench.py --impl reference`` can time the reference's own
+CPU path, and so that ``tests/test_dropin_examples_gpu.py`` can run the reference's unmodified example
+drivers against the ``eigd`` alias of this repository.  The tree it loads is ``baseline/_ref`` (offline
+install made by ``baseline/install_reference.py``; git-ignored, shipped to the GPU box) and, only in the
+build container and as a last resort, ``/root/reference``.  Nothing in the product imports this file.
 """
+import importlib
 import importlib.util
 import os
 import sys
@@ -23,7 +27,22 @@ from unittest import mock
 
 import numpy as np
 
-REF_ROOT = os.environ.get("EIGD_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _default_root():
+    """EIGD_REFERENCE_ROOT, else the offline install baseline/_ref (baseline/install_reference.py: the copy that
+    travels to the GPU box), else the build container's read-only /root/reference."""
+    env = os.environ.get("EIGD_REFERENCE_ROOT")
+    if env:
+        return env
+    for cand in (os.path.join(_REPO, "baseline", "_ref"), "/root/reference"):
+        if os.path.isfile(os.path.join(cand, "eigd", "eigenvector_derivatives.py")):
+            return cand
+    return "/root/reference"
+
+
+REF_ROOT = _default_root()
 
 
 def reference_available():
@@ -92,12 +111,19 @@ def install_matplotlib_stub():
     sys.modules["matplotlib"] = mpl
 
 
+_LOADED = {}
+
+
 def load_reference(force=False):
     """Return the reference ``eigd`` package (module object) loaded from REF_ROOT."""
     if not reference_available():
         raise RuntimeError("reference tree not present at %s" % REF_ROOT)
     if not force and getattr(sys.modules.get("eigd"), "_is_reference", False):
         return sys.modules["eigd"]
+    if not force and _LOADED:
+        for k, v in _LOADED.items():
+            sys.modules[k] = v
+        return _LOADED["eigd"]
     from scipy.sparse.linalg import LinearOperator
 
     pkg = types.ModuleType("eigd")
@@ -105,10 +131,12 @@ def load_reference(force=False):
     pkg._is_reference = True
     sys.modules["eigd"] = pkg
     sys.modules["eigd.arpack"] = _make_arpack_module()
+    sys.modules["eigd.arpack"]._is_reference = True
     spec = importlib.util.spec_from_file_location(
         "eigd.eigenvector_derivatives", os.path.join(REF_ROOT, "eigd", "eigenvector_derivatives.py"))
     ed = importlib.util.module_from_spec(spec)
     ed.__package__ = "eigd"
+    ed._is_reference = True
     sys.modules["eigd.eigenvector_derivatives"] = ed
     spec.loader.exec_module(ed)
     _orig = ed.SpLuOperator.__init__
@@ -124,21 +152,54 @@ def load_reference(force=False):
     pkg.arpack = sys.modules["eigd.arpack"]
     pkg.eigenvector_derivatives = ed
     pkg.__version__ = "1.0.0"
+    _LOADED.update({"eigd": pkg, "eigd.arpack": pkg.arpack, "eigd.eigenvector_derivatives": ed})
     return pkg
 
 
-def load_example(name):
-    """Import reference examples/<name>.py (not as __main__) with the shimmed eigd."""
-    load_reference()
+def load_example(name, against="reference"):
+    """Import reference examples/<name>.py (not as __main__).
+
+    against="reference": with the shimmed reference ``eigd`` (golden generation, the CPU reference arm).
+    against="alias":     with ``eigd`` resolving to this repository's drop-in alias package (``eigd/`` at the
+                         repo root -> eigd_b200), i.e. the unmodified example driver on the GPU path.
+    The example binds its ``eigd`` names at import time, so the two flavours can coexist in one process."""
     install_matplotlib_stub()
     exdir = os.path.join(REF_ROOT, "examples")
+    if not os.path.isfile(os.path.join(exdir, name + ".py")):
+        raise RuntimeError("reference example %s.py not present under %s" % (name, exdir))
     if exdir not in sys.path:
         sys.path.insert(0, exdir)
-    modname = "_ref_example_" + name
+    modname = ("_ref_example_" if against == "reference" else "_alias_example_") + name
     if modname in sys.modules:
         return sys.modules[modname]
-    spec = importlib.util.spec_from_file_location(modname, os.path.join(exdir, name + ".py"))
-    mod = importlib.util.module_from_spec(spec)
-    sys.modules[modname] = mod
-    spec.loader.exec_module(mod)
+    names = ("eigd", "eigd.arpack", "eigd.eigenvector_derivatives")
+    saved = {k: sys.modules.get(k) for k in names}
+    try:
+        if against == "reference":
+            load_reference()                     # registers the reference under the three names
+        elif against == "alias":
+            for k in names:
+                if getattr(sys.modules.get(k), "_is_reference", False) or k != "eigd":
+                    sys.modules.pop(k, None)
+            if getattr(sys.modules.get("eigd"), "_is_reference", False):
+                sys.modules.pop("eigd")
+            if _REPO not in sys.path:
+                sys.path.insert(0, _REPO)
+            alias = importlib.import_module("eigd")
+            if getattr(alias, "_is_reference", False) or "eigd_b200" not in getattr(alias.IRAM, "__module__", ""):
+                raise RuntimeError("eigd did not resolve to the alias package of this repository")
+        else:
+            raise ValueError(against)
+        spec = importlib.util.spec_from_file_location(modname, os.path.join(exdir, name + ".py"))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[modname] = mod
+        spec.loader.exec_module(mod)
+    finally:
+        for k, v in saved.items():               # leave sys.modules["eigd"...] as the caller had it
+            if v is not None:
+                sys.modules[k] = v
+            elif against == "alias":
+                pass                             # the alias is the importable `eigd` of this repository: keep it
+            else:
+                sys.modules.pop(k, None)
     return mod

@@ -1,6 +1,6 @@
 """World-size-2 gloo tests (CPU) of the multi-GPU host logic in eigd_b200/dist.py: the per-mode column
-shards, the contiguous element ranges, the two gathers of the sharded adjoint and the merge of the
-per-mode host scalars.  The sharded solvers themselves run on GPUs (bench.py --gpus N)."""
+shards, the contiguous element ranges and the one packed all-gather of the sharded adjoint (columns of psi
+plus the per-mode host scalars).  The sharded solvers themselves run on GPUs (bench.py --gpus N)."""
 import os
 import socket
 import sys
@@ -48,11 +48,19 @@ def _worker(rank, world, port, n, N, nelems, out):
         assert max(h - l for l, h in ranges) - min(h - l for l, h in ranges) <= 1
         vec = torch.arange(nelems, dtype=torch.float64) ** 2
         assert torch.equal(sh.allgather_ranges(vec[lo:hi].clone(), nelems), vec)
-        # per-mode host data (G columns, info, residual histories)
-        G = np.arange(N * N, dtype=float).reshape(N, N)
-        parts = sh.allgather_object((G[:, cols], [int(c) for c in cols]))
-        assert np.array_equal(sh.merge_cols_host([p[0] for p in parts], N), G)
-        assert sorted(sum((p[1] for p in parts), [])) == list(range(N))
+        # per-mode host data (G columns, info, residual histories) ride in the SAME all-gather as the columns
+        G = np.arange(N * N, dtype=float).reshape(N, N) + 0.25
+        info = [int(3 + c) for c in cols]
+        hist = [[1.0 / (k + 1 + c) for k in range(2 + int(c) % 3)] for c in cols]
+        packed = sh.pack_mode_scalars(N, G[:, cols], info, hist)
+        got2, extras = sh.allgather_cols(mine, N, extra=packed)
+        assert torch.equal(got2, full)
+        G2, info2, hist2 = sh.unpack_mode_scalars(N, extras)
+        assert np.array_equal(G2, G)
+        assert info2 == [3 + i for i in range(N)]
+        assert hist2 == [[1.0 / (k + 1 + i) for k in range(2 + i % 3)] for i in range(N)]
+        st = sh.collective_stats()
+        assert st["calls"] == 3 and st["bytes"] > 0 and sh.collective_stats()["calls"] == 0
         # max over ranks of a per-rank timing, as bench.py does it
         t = torch.tensor([float(rank + 1)], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -1,5 +1,6 @@
 // Developer micro-benchmark: cost of a software grid barrier on B200 (cooperative launch).
-// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/bench_barrier tools/bench_barrier.cu
+// nvcc --cudart shared -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/bench_barrier tools/bench_barrier.cu
+// (build on the GPU box into /tmp or gpurun_out/: binaries are never kept in the tree)
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstdlib>

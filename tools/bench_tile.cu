@@ -1,6 +1,6 @@
 // Developer micro-benchmark: latency anatomy of ONE top-level solve tile (16 warps: 32 strided panel loads per
 // lane from cold HBM, three ld.cg gathers of data written just before by other SMs, shared-memory staging,
-// 32 dependent FMAs).  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/bench_tile.bin tools/bench_tile.cu
+// 32 dependent FMAs).  nvcc --cudart shared -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/bench_tile tools/bench_tile.cu
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstdlib>
