@@ -3,38 +3,43 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--nx NX] [--modes NM]
 
-Workload (config.workload): BASELINE.json configs[1] -- the thermal eigenproblem of
-examples/thermal.py at nx = ny = 500 (251 001 DOF), 10 modes, m = 60, sigma = -0.1, IRAM + sibk
-(lanczos_guess, rtol 1e-10), tensor derivative, modal thermal-compliance objective; synthetic
-design x ~ U(0.3, 1) (breaks the symmetric-pair degeneracy of the uniform square).
-A "step" is one pass design -> gradient: filter, material, K/M assembly, numeric LDL^T of
-K - sigma M, eigensolve, adjoint right-hand sides, adjoint solve, df/dx, node gather, filter^T.
+Workload (config.workload): BASELINE.json configs[1] -- the thermal eigenproblem of examples/thermal.py at
+nx = ny = 500 (251 001 DOF), 10 modes, m = 60, sigma = -0.1, IRAM + sibk (lanczos_guess, rtol 1e-10), tensor
+derivative, modal thermal-compliance objective; synthetic design x ~ U(0.3, 1) (breaks the symmetric-pair
+degeneracy of the uniform square).  A "step" is one pass design -> gradient: filter, material, K/M
+assembly, numeric LDL^T of K - sigma M, eigensolve, adjoint right-hand sides, adjoint solve, df/dx, node gather,
+filter^T.  Parity of exactly this call against the unmodified reference: tests/test_fullsize_golden_gpu.py.
 
 value   : seconds per gradient with the design already in HBM (CUDA events, sum over K steps / K).
-e2e     : seconds per gradient through the reference-facing numpy API: host scipy CSR K, M in,
-          host df/dx out, every host<->device copy inside the timed region.
-N > 1   : strong scaling -- eigensolve replicated, per-mode adjoint solves sharded round robin,
-          element ranges of df/dx sharded (eigd_b200/dist.py); max over ranks.
---impl reference : the CPU path of the reference (oracle port: scipy SuperLU + ARPACK + numpy) on
-          the host cores, bounded sample per step (see cpu_reference()).
+e2e     : seconds per gradient through the reference-facing numpy API: host scipy CSR K, M in, host df/dx out,
+          every host<->device copy inside the timed region.
+N > 1   : ONE design, strong scaling -- factorisation and eigensolve replicated (they do not shard),
+          per-mode adjoint solves sharded round robin with one packed all-gather, element ranges of df/dx sharded
+          with one all-gather (eigd_b200/dist.py); max over ranks.  The line also carries, as top-level keys,
+          `c3_buckling` (configs[2]: 497k-DOF buckling, 20 modes, adjoints sharded per mode) and `c5_sweep`
+          (configs[4]: 64 filtered designs of the 202k-DOF natural-frequency mesh spread over the GPUs, no data-path
+          collective until the final gather of the gradients) -- also at N = 1, where they are the base of the curves.
+--impl reference : the reference's OWN CPU path on the box's host cores -- the unmodified examples/thermal.py driver
+          from baseline/_ref (make_model -> initialize -> thermal-compliance seeds -> finalize_adjoint) when that
+          offline install is present (kind "reference"), else the oracle port (kind "port").  Every step is one
+          complete gradient at full size; as many of the requested steps as fit a time budget are run and the line
+          reports the steps actually run.
 """
 import argparse
 import json
 import os
 import subprocess
 import sys
-import threading
 import time
+import warnings
 
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-SIGMA, MLANCZOS = -0.1, 60
-# operation counts of the unmodified reference on this exact configuration, measured in the build
-# container through oracle/ref_loader.py (SURVEY.md section 6, thermal nx=ny=500, N=10, m=60)
-REF_EIG_SOLVES, REF_ADJ_SOLVES, REF_B_PER_EIG_SOLVE = 61, 214, 3
+SIGMA, MLANCZOS, RTOL = -0.1, 60, 1e-10
+X_SEED, VEC_SEED = 0, 12345
 
 
 def parse():
@@ -47,105 +52,165 @@ def parse():
     ap.add_argument("--modes", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-API leg")
-    ap.add_argument("--shard", default="designs", choices=["designs", "modes"],
-                    help="N > 1: 'designs' = one independent design per GPU (weak scaling, no data-path collective); "
-                         "'modes' = one design, per-mode adjoint solves and df/dx element ranges sharded (strong scaling)")
-    ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the extra strong-scaling measurement")
+    ap.add_argument("--no-extras", action="store_true", help="skip the c3_buckling / c5_sweep legs")
+    ap.add_argument("--c5-designs", type=int, default=64)
+    ap.add_argument("--ref-budget", type=float, default=150.0,
+                    help="--impl reference: seconds of timed CPU steps (at least one full gradient is always run)")
+    ap.add_argument("--ref-kind", default="auto", choices=["auto", "reference", "port"])
     return ap.parse_args()
 
 
 # ------------------------------------------------------------------------------------------
-# CPU reference arm (oracle port of the reference path; the only place the product tree runs oracle/)
+# CPU arms: the reference itself (baseline/_ref) or the oracle port, one complete gradient per step
 # ------------------------------------------------------------------------------------------
-class CpuReference:
-    """Bounded sample of the reference's CPU path at FULL problem size.
+class CpuGradient:
+    """The bench workload on the host cores, through the reference's own code path.
 
-    The unmodified reference needs ~80 s per gradient on this workload, so one
-    step times a slice of it and scales by the reference's own operation counts:
-      setup (timed once, added to every step): SuperLU factorisation of K - sigma M (splu);
-      per step: S SuperLU solves, S B-products (the two operations 90 % of the reference's time
-      goes to), one full evaluation of the dK/dM einsum callbacks for N modes;
-      value = t_factor + (61 + 214) * t_solve + (3*61 + 214 + 2N + m) * t_spmv + t_dfdx.
-    Krylov orthogonalisation and Python overhead of the reference are NOT included, so the number
-    is a lower bound on the reference's time-to-gradient."""
+    kind "reference": unmodified examples/thermal.py + eigd/eigenvector_derivatives.py from baseline/_ref, loaded by
+        oracle/ref_loader.py (scipy >= 1.15 shim for eigd/arpack.py only).  Timed: ThermalTopologyAnalysis.initialize
+        (filter, assembly, splu, IRAM.solve: examples/thermal.py:268-342), add_thermal_compliance_derivative (:436-442),
+        finalize_adjoint (sibk with lanczos_guess, add_total_derivative tensor, node scatter, filter^T: :560-623).
+        Untimed one-off setup: make_model (the reference builds its filter with a Python loop over the nodes).
+    kind "port": the numpy restatement (oracle/eigd_oracle.py, fe_oracle.py) of the same calls -- same scipy SuperLU /
+        ARPACK / LAPACK underneath, vectorised setup.
+    Both are single-process; scipy's SuperLU and ARPACK are sequential, numpy's BLAS uses the host's threads."""
 
-    def __init__(self, nx, N):
+    def __init__(self, nx, N, kind="auto", rtol=RTOL):
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
-        import eigd_oracle as eo
-        import fe_oracle as fo
-        self.N = N
-        conn, X = fo.grid_mesh(nx, nx, 1.0, 1.0)
-        self.mdl = fo.Q4Model(conn, X, "thermal")
-        rng = np.random.default_rng(0)
-        self.rhoE = rng.uniform(0.3, 1.0, self.mdl.nelems)
-        self.K, self.M = self.mdl.assemble(self.rhoE)
+        ref_root = os.path.join(ROOT, "baseline", "_ref")
+        have_ref = os.path.isfile(os.path.join(ref_root, "examples", "thermal.py"))
+        if kind == "auto":
+            kind = "reference" if have_ref else "port"
+        if kind == "reference" and not have_ref:
+            raise RuntimeError("baseline/_ref is not installed (python baseline/install_reference.py)")
+        self.kind, self.nx, self.N, self.rtol = kind, nx, N, rtol
+        nnodes = (nx + 1) ** 2
+        self.x = np.random.default_rng(X_SEED).uniform(0.3, 1.0, nnodes)
+        self.vec = np.random.default_rng(VEC_SEED).uniform(size=nnodes)
         t0 = time.perf_counter()
-        self.factor = eo.SpLu(self.K - SIGMA * self.M)
-        self.t_factor = time.perf_counter() - t0
-        self.rng = rng
-        self.n = self.K.shape[0]
+        if kind == "reference":
+            os.environ["EIGD_REFERENCE_ROOT"] = ref_root          # never /root/reference at run time
+            import ref_loader as rl
+            rl.REF_ROOT = ref_root
+            th = rl.load_example("thermal")
+            self.topo = th.make_model(nx=nx, ny=nx, N=N, m=MLANCZOS, sigma=SIGMA, solver_type="IRAM", adjoint_method="sibk",
+                                      adjoint_options={"lanczos_guess": True, "update_guess": False, "bs_target": 1},
+                                      rtol=rtol, deriv_type="tensor")
+        else:
+            import eigd_oracle as eo
+            import fe_oracle as fo
+            self.eo = eo
+            conn, X = fo.grid_mesh(nx, nx, 1.0, 1.0)
+            self.mdl = fo.Q4Model(conn, X, "thermal")
+            self.fltr = fo.ConicFilter(X, 4.0 * (1.0 / nx))
+        self.setup_s = time.perf_counter() - t0
+        self.stages = {}
+        self.counts = {}
 
-    def step(self, S=3):
-        n, N = self.n, self.N
-        b = self.rng.normal(size=n)
+    def step(self):
+        """One complete gradient; returns wall seconds of the whole pass."""
         t0 = time.perf_counter()
-        for _ in range(S):
-            b = self.factor(b)
-        t_solve = (time.perf_counter() - t0) / S
-        t0 = time.perf_counter()
-        for _ in range(S):
-            b = self.M @ b
-        t_spmv = (time.perf_counter() - t0) / S
-        W = self.rng.normal(size=(n, N))
-        V = self.rng.normal(size=(n, N))
-        t0 = time.perf_counter()
-        self.mdl.dK(self.rhoE, W, V)
-        self.mdl.dM(self.rhoE, W, V)
-        t_dfdx = time.perf_counter() - t0
-        nspmv = REF_B_PER_EIG_SOLVE * REF_EIG_SOLVES + REF_ADJ_SOLVES + 2 * N + MLANCZOS
-        total = self.t_factor + (REF_EIG_SOLVES + REF_ADJ_SOLVES) * t_solve + nspmv * t_spmv + t_dfdx
-        self.last = {"t_factor": self.t_factor, "t_solve": t_solve, "t_spmv": t_spmv, "t_dfdx": t_dfdx}
-        return total
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            if self.kind == "reference":
+                topo = self.topo
+                topo.x[:] = self.x
+                topo.initialize()
+                topo.initialize_adjoint()
+                topo.add_thermal_compliance_derivative(1.0, self.vec)
+                topo.finalize_adjoint()
+                p = topo.profile
+                self.stages = {k: float(p[k]) for k in ("matrix assembly time", "eigenvalue solve time",
+                                                        "adjoint solution time", "total derivative time")}
+                self.counts = {"eig_solves": int(p["solve preconditioner count"]),
+                               "adjoint_solves": int(p["adjoint preconditioner count"])}
+                self.xb = topo.xb
+            else:
+                eo, mdl = self.eo, self.mdl
+                ta = time.perf_counter()
+                rho = self.fltr.apply(self.x)
+                rhoE = mdl.element_density(rho)
+                K, M = mdl.assemble(rhoE)
+                tb = time.perf_counter()
+                f = eo.SpLu((K - SIGMA * M).tocsc())
+                s = eo.IRAMOracle(N=self.N, m=MLANCZOS)
+                lam, Phi = s.solve(K, M, f, SIGMA, rng=0)
+                n_eig = f.count
+                tc = time.perf_counter()
+                c = Phi.T @ self.vec
+                Phib = 2.0 * np.outer(self.vec, c / lam)
+                lamb = -(c * c) / lam**2
+                Phib[:, 0], lamb[0] = 0.0, 0.0
+                f.count = 0
+                psi, data = s.solve_adjoint(Phib, method="sibk", rtol=self.rtol, lanczos_guess=True)
+                td = time.perf_counter()
+                dfdx = np.zeros(mdl.nelems)
+                eo.add_total_derivative(lam, Phi, lamb, Phib, psi, lambda w, v: mdl.dK(rhoE, w, v),
+                                        lambda w, v: mdl.dM(rhoE, w, v), dfdx, data, "normal")
+                self.xb = self.fltr.apply_gradient(mdl.scatter_to_nodes(dfdx))
+                te = time.perf_counter()
+                self.stages = {"matrix assembly time": tb - ta, "eigenvalue solve time": tc - tb,
+                               "adjoint solution time": td - tc, "total derivative time": te - td}
+                self.counts = {"eig_solves": int(n_eig), "adjoint_solves": int(f.count)}
+        return time.perf_counter() - t0
 
-    def describe(self, S=3):
-        return ("full-size %d-DOF K, M; splu factor timed once (%.2f s); per step %d SuperLU solves, %d B-products, "
-                "one dK/dM einsum pass for N=%d, scaled by the reference's measured counts (%d+%d solves); "
-                "orthogonalisation and Python overhead excluded (lower bound)"
-                % (self.n, self.t_factor, S, S, self.N, REF_EIG_SOLVES, REF_ADJ_SOLVES))
+    def describe(self, steps):
+        what = ("unmodified reference (baseline/_ref: examples/thermal.py driver + eigd/eigenvector_derivatives.py, scipy "
+                "SuperLU + ARPACK)" if self.kind == "reference" else
+                "oracle port (oracle/eigd_oracle.py + fe_oracle.py: numpy restatement on the same scipy SuperLU + ARPACK)")
+        return ("%s; %d complete gradient(s) at full size (%d DOF, N=%d, m=%d, rtol %.0e): filter, assembly, splu, IRAM, "
+                "sibk + lanczos_guess, tensor derivative, filter^T; one-off setup %.1f s not included"
+                % (what, steps, (self.nx + 1) ** 2, self.N, MLANCZOS, self.rtol, self.setup_s))
+
+
+def host_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        n = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+    except Exception:
+        n = 1
+    return int(n)
 
 
 def run_reference(args, rank):
+    """The reference arm: rank 0 alone runs it, the other ranks exit without work."""
     if rank != 0:
         return
-    ref = CpuReference(args.nx, args.modes)
-    for _ in range(args.warmup):
-        ref.step()
-    vals = [ref.step() for _ in range(args.steps)]
+    try:
+        ref = CpuGradient(args.nx, args.modes, kind=args.ref_kind)
+    except Exception as exc:                     # pragma: no cover
+        print(json.dumps({"impl": "reference", "unavailable": "%s: %s" % (type(exc).__name__, exc)}))
+        return
+    # every step is a complete gradient (tens of seconds): no separate warm-up pass (a CPU path has nothing to warm that a
+    # 30 s step would not amortise), and as many of the requested steps as fit the budget -- at least one
+    vals, spent = [], 0.0
+    while len(vals) < max(1, args.steps) and (not vals or spent + vals[-1] <= args.ref_budget):
+        vals.append(ref.step())
+        spent += vals[-1]
     v = float(np.mean(vals))
-    line = base_line(args, v, v * 1e3)
-    line.update({"impl": "reference", "n_gpus": args.gpus, "gpu_launches": 0,
-                 "cpu_baseline": {"value": v, "unit": "s", "cores": 1, "kind": "port", "sample": ref.describe(),
-                                  "detail": ref.last},
+    line = base_line(args, v, v * 1e3, world=1)
+    line.update({"impl": "reference", "n_gpus": args.gpus, "gpu_launches": 0, "steps": len(vals), "warmup": 0,
+                 "steps_requested": args.steps, "warmup_requested": args.warmup, "per_step_s": vals,
+                 "stages_s": ref.stages, "counts": ref.counts, "setup_s": ref.setup_s,
+                 "cpu_baseline": {"value": v, "unit": "s", "cores": host_threads(), "host_cpus": os.cpu_count(),
+                                  "kind": ref.kind, "sample": ref.describe(len(vals))},
                  "e2e": {"value": v, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    line["config"]["parallelism"] = "host CPU, 1 process (rank 0)"
     print(json.dumps(line))
 
 
-def base_line(args, value, ms):
+def base_line(args, value, ms, world):
     n = (args.nx + 1) ** 2
-    weak = args.gpus > 1 and args.shard == "designs"
     return {"metric": "time_to_gradient", "value": value, "unit": "s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False, "scaling": "weak" if weak else "strong",
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "thermal_q4_nx%d_ny%d_%ddof_N%d_m%d_iram_sibk" % (args.nx, args.nx, n, args.modes, MLANCZOS),
                        "baseline_config": "configs[1]: examples/thermal.py scaled to ~250k DOF, 10 modes, single B200",
-                       "sigma": SIGMA, "rtol": 1e-10, "deriv_type": "tensor",
+                       "sigma": SIGMA, "rtol": RTOL, "deriv_type": "tensor",
                        "l2": "explicit 256 MiB L2 flush between timed steps; per-step working set ~1 GB > 126 MB L2",
-                       "parallelism": "1 GPU" if args.gpus == 1 else
-                       ("design-batch sweep (BASELINE configs[4] pattern): %d independent designs of the same mesh, one per "
-                        "GPU, no data-path collective; value = step time (max over ranks) / %d designs" % (args.gpus, args.gpus)
-                        if weak else
-                        "one design: eigensolve replicated, per-mode adjoint + element-range dfdx sharded over %d GPUs"
-                        % args.gpus)}}
+                       "parallelism": "1 GPU" if world == 1 else
+                       "one design: factorisation + eigensolve replicated (do not shard), per-mode adjoint solves (mode i -> rank "
+                       "i mod %d, one packed all-gather) + element-range df/dx (one all-gather) sharded over %d GPUs" % (world, world)}}
 
 
 # ------------------------------------------------------------------------------------------
@@ -191,6 +256,138 @@ class Clocks:
 
 
 # ------------------------------------------------------------------------------------------
+# the other BASELINE configurations, as extra keys of the line
+# ------------------------------------------------------------------------------------------
+def golden_scalar(name, key):
+    try:
+        return float(np.load(os.path.join(ROOT, "tests", "golden", "fullsize_%s.npz" % name))[key])
+    except Exception:
+        return None
+
+
+def pert_dot(xb):
+    import torch
+    pert = np.random.default_rng(777).uniform(size=xb.shape[0])
+    return float((xb * torch.as_tensor(pert, device=xb.device)).sum().item())
+
+
+def run_c3(shard, rank, world, barrier, reps=2):
+    """BASELINE configs[2]: examples/buckling.py at nx=352, ny=704 (497 024 DOF), 20 modes, sigma=3 (indefinite), adjoint
+    modes sharded over the ranks.  Strong scaling of one gradient; parity against tests/golden/fullsize_c3.npz."""
+    import torch
+    import torch.distributed as dist
+    from eigd_b200 import topo as T
+    t0 = time.perf_counter()
+    model = T.make_buckling_model(nx=352, ny=704, N=20, m=60, sigma=3.0, solver_type="IRAM", adjoint_method="sibk",
+                                  adjoint_options={"lanczos_guess": True}, rtol=RTOL, deriv_type="tensor")
+    setup = time.perf_counter() - t0
+    model.sharding = shard
+    node = int(np.load(os.path.join(ROOT, "tests", "golden", "fullsize_c3.npz"))["node"]) \
+        if os.path.isfile(os.path.join(ROOT, "tests", "golden", "fullsize_c3.npz")) else 2 * (model.nnodes // 2) + 1
+    out = []
+    for rep in range(reps + 1):
+        if shard is not None:
+            shard.collective_stats()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            model.initialize()
+        model.initialize_adjoint()
+        model.add_eigenvector_aggregate_derivative(1.0, 100.0, node, mode="tanh")
+        model.finalize_adjoint()
+        e1.record()
+        torch.cuda.synchronize()
+        p = model.profile
+        coll = shard.collective_stats() if shard is not None else {"calls": 0, "ms": 0.0, "bytes": 0}
+        vals = [e0.elapsed_time(e1) / 1e3, p["matrix assembly time"], p["eigenvalue solve time"], p["adjoint solution time"],
+                p["total derivative time"], coll["ms"] / 1e3]
+        if world > 1:
+            t = torch.tensor(vals, dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            vals = t.tolist()
+        if rep:                                   # rep 0 warms up (symbolic analysis, allocator)
+            out.append(vals + [coll["bytes"], coll["calls"]])
+    best = min(out, key=lambda v: v[0])
+    d = pert_dot(model.xb)
+    gold = golden_scalar("c3", "pert_dot_xb")
+    return {"config": "configs[2]: buckling nx=352 ny=704, %d DOF, N=20, m=60, sigma=3.0 (indefinite), IRAM + sibk, rtol %.0e"
+                      % (model.prob.nred, RTOL),
+            "scaling": "strong", "n_gpus": world, "value": best[0], "unit": "s",
+            "stages_s_max_over_ranks": {"matrix assembly (incl. fundamental path)": best[1], "eigenvalue solve (replicated)": best[2],
+                                        "adjoint solution (sharded per mode)": best[3], "total derivative": best[4]},
+            "time_to_gradient_s": best[2] + best[3] + best[4],
+            "allgather": {"s": best[5], "bytes": int(best[6]), "calls": int(best[7])},
+            "eig_solves": model.profile["solve preconditioner count"], "adjoint_solves_this_rank": model.profile["adjoint preconditioner count"],
+            "refine_steps": model.factor.refine, "factor_info": model.factor.info,
+            "pert_dot_xb": d, "reference_pert_dot_xb": gold,
+            "rel_err_vs_reference": (abs(d - gold) / abs(gold)) if gold else None,
+            "limit": "the replicated eigensolve + factorisation (Amdahl) and the k = ceil(20 / N)-column solve, which is "
+                     "latency-bound below ~4 columns", "host_setup_s": setup}
+
+
+def run_c5(rank, world, barrier, ndesigns):
+    """BASELINE configs[4]: `ndesigns` filtered density fields on the 448 x 224 natural-frequency mesh (202 050 DOF, N = 6 + 3
+    rigid-body modes), design b -> rank b mod world, no data-path collective; one all-gather of the gradients at the end."""
+    import torch
+    import torch.distributed as dist
+    from eigd_b200 import device as D, topo as T
+    t0 = time.perf_counter()
+    model = T.make_natural_frequency_model(nx=448, ny=224, Lx=2.0, Ly=1.0, N=6, m=60, sigma=-10.0, solver_type="IRAM",
+                                           adjoint_method="sibk", adjoint_options={"lanczos_guess": True}, rtol=RTOL,
+                                           deriv_type="tensor")
+    setup = time.perf_counter() - t0
+    ndv = model.fltr.num_design_vars
+    w_d = D.to_device(np.random.default_rng(99).normal(size=(model.nvars, 6)))
+    mine = list(range(rank, ndesigns, world))
+    xs = [D.to_device(np.random.default_rng(b).uniform(0.3, 1.0, ndv)) for b in mine]
+    grads = torch.zeros((max(1, (ndesigns + world - 1) // world), ndv), dtype=torch.float64, device="cuda")
+
+    def sweep():
+        for i, x_d in enumerate(xs):
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                model.initialize(x=x_d)
+            model.initialize_adjoint()
+            model.add_modal_function_derivative(w_d)
+            model.finalize_adjoint()
+            grads[i].copy_(model.xb)
+        if world > 1:
+            allg = torch.empty((world,) + tuple(grads.shape), dtype=torch.float64, device="cuda")
+            dist.all_gather_into_tensor(allg.view(-1), grads.view(-1))
+            return allg
+        return grads.unsqueeze(0)
+
+    xs_warm, xs[:] = xs[:], xs[:1]
+    sweep()                                        # warm-up on one design (symbolic analysis, allocator)
+    xs[:] = xs_warm
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    allg = sweep()
+    e1.record()
+    torch.cuda.synchronize()
+    secs = e0.elapsed_time(e1) / 1e3
+    if world > 1:
+        t = torch.tensor([secs], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        secs = float(t[0])
+    d = pert_dot(allg[0, 0])                      # design 0 lives on rank 0, slot 0
+    gold = golden_scalar("c5", "pert_dot_xb")
+    p = model.profile
+    return {"config": "configs[4]: %d designs x ~ U(0.3, 1) (default_rng(b)), natural_frequency.make_model(nx=448, ny=224), "
+                      "%d DOF, N=6 (+3 rigid-body modes), m=60, sigma=-10, IRAM + sibk, rtol %.0e" % (ndesigns, model.nvars, RTOL),
+            "scaling": "strong (fixed sweep of %d designs spread over the GPUs)" % ndesigns, "n_gpus": world,
+            "value": secs, "unit": "s per sweep", "s_per_design": secs / ndesigns, "designs_per_s": ndesigns / secs,
+            "last_design_stages_s": {k: p[k] for k in ("matrix assembly time", "eigenvalue solve time", "adjoint solution time",
+                                                       "total derivative time")},
+            "gradients_allgather_bytes": int(allg.numel() * 8) if world > 1 else 0,
+            "design0_pert_dot_xb": d, "reference_pert_dot_xb": gold,
+            "rel_err_vs_reference": (abs(d - gold) / abs(gold)) if gold else None, "host_setup_s": setup}
+
+
+# ------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------
 def run_ours(args, rank, world):
@@ -203,18 +400,15 @@ def run_ours(args, rank, world):
     torch.cuda.set_device(local)
     D.init("cuda:%d" % local)
     shard = None
-    designs = world > 1 and args.shard == "designs"
-    if world > 1 and not designs:
+    if world > 1:
         from eigd_b200.dist import ModeSharding
         shard = ModeSharding()
     N = args.modes
     model = T.make_thermal_model(nx=args.nx, ny=args.nx, N=N, m=MLANCZOS, sigma=SIGMA, solver_type="IRAM",
-                                 adjoint_method="sibk", adjoint_options={"lanczos_guess": True}, rtol=1e-10,
+                                 adjoint_method="sibk", adjoint_options={"lanczos_guess": True}, rtol=RTOL,
                                  deriv_type="tensor", seed=0)
-    model.sharding = shard
-    rng = np.random.default_rng(rank if designs else 0)     # designs mode: rank r evaluates design r
-    x_h = rng.uniform(0.3, 1.0, model.nnodes)
-    vec_h = np.random.default_rng(12345).uniform(size=model.nnodes)
+    x_h = np.random.default_rng(X_SEED).uniform(0.3, 1.0, model.nnodes)       # the same design on every rank
+    vec_h = np.random.default_rng(VEC_SEED).uniform(size=model.nnodes)
     x_d, vec_d = D.to_device(x_h), D.to_device(vec_h)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
@@ -230,12 +424,32 @@ def run_ours(args, rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- parity inside the run: against the frozen reference output, and sharded against unsharded ----------
+    model.sharding = None
+    xb_single = step_device().clone()
+    parity = {"pert_dot_xb": pert_dot(xb_single)}
+    if args.nx == 500 and N == 10:
+        gold = golden_scalar("c2", "pert_dot_xb")
+        parity["reference_pert_dot_xb"] = gold
+        parity["rel_err_vs_reference"] = (abs(parity["pert_dot_xb"] - gold) / abs(gold)) if gold else None
+        try:
+            gx = np.load(os.path.join(ROOT, "tests", "golden", "fullsize_c2.npz"))["xb"]
+            parity["xb_max_rel_err_vs_reference"] = float(np.abs(xb_single.cpu().numpy() - gx).max() / np.abs(gx).max())
+        except Exception:
+            pass
+    model.sharding = shard
+    if shard is not None:
+        xb_sh = step_device()
+        parity["sharded_rel_err"] = float(((xb_sh - xb_single).abs().max() / xb_single.abs().max()).item())
+
     for _ in range(max(args.warmup, 1)):
         step_device()
     barrier()
     clocks = Clocks(local)
     if rank == 0:
         clocks.start()
+    if shard is not None:
+        shard.collective_stats()
     D.Timeline.reset()
     D.Timeline.enabled = True
     D.solve_timing_begin()                  # native-side CUDA events around every solve launch of the timed region
@@ -243,73 +457,25 @@ def run_ours(args, rank, world):
     evs = []
     stage = {"eigenvalue solve time": 0.0, "adjoint solution time": 0.0, "total derivative time": 0.0,
              "matrix assembly time": 0.0}
-    prof = None
-    if os.environ.get("EIGD_BENCH_CPROFILE"):
-        import cProfile
-        prof = cProfile.Profile()
     for _ in range(args.steps):
         flush.fill_(1)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        if prof:
-            prof.enable()
         step_device()
-        if prof:
-            torch.cuda.synchronize()
-            prof.disable()
         e1.record()
         evs.append((e0, e1))
         torch.cuda.synchronize()
         for k in stage:
             stage[k] += model.profile[k] / args.steps
     barrier()
-    if prof:
-        import pstats
-        pstats.Stats(prof, stream=sys.stderr).sort_stats("tottime").print_stats(18)
     launches = D.launch_count() - l0
     solve_by_k = D.solve_timing_end()
     D.Timeline.enabled = False
     tl = D.Timeline.summary()
+    coll = shard.collective_stats() if shard is not None else None
     per_step_ms = [a.elapsed_time(b) for a, b in evs]
     ms = sum(per_step_ms) / args.steps
-    # ---- N > 1, designs mode: also time ONE design with the sharded stages (strong scaling) -----------
-    strong = None
-    if designs and not args.no_strong:
-        from eigd_b200.dist import ModeSharding
-        sh = ModeSharding()
-        x0_d = D.to_device(np.random.default_rng(0).uniform(0.3, 1.0, model.nnodes))   # same design on every rank
-        model.sharding = sh
-
-        def step_strong():
-            model.initialize(x=x0_d)
-            model.initialize_adjoint()
-            model.add_thermal_compliance_derivative(1.0, vec_d)
-            model.finalize_adjoint()
-
-        for _ in range(2):
-            step_strong()
-        tms = []
-        stage_s = {"eigenvalue solve time": 0.0, "adjoint solution time": 0.0, "total derivative time": 0.0}
-        for _ in range(args.steps):
-            flush.fill_(1)
-            barrier()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            step_strong()
-            e1.record()
-            torch.cuda.synchronize()
-            tms.append(e0.elapsed_time(e1))
-            for k in stage_s:
-                stage_s[k] += model.profile[k] / args.steps
-        barrier()
-        t = torch.tensor([sum(tms) / len(tms)] + [stage_s[k] for k in sorted(stage_s)], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        strong = {"value": float(t[0]) / 1e3, "unit": "s", "scaling": "strong",
-                  "parallelism": "one design: eigensolve + factorisation replicated, per-mode adjoint solves (mode i -> "
-                                 "rank i mod N, one all-gather) and df/dx element ranges (one all-gather) sharded",
-                  "stages_s_max_over_ranks": {k: float(v) for k, v in zip(sorted(stage_s), t[1:].tolist())}}
-        model.sharding = None
     # ---- end to end through the numpy API (host CSR in, host df/dx out) ---------------------------
     K_h, M_h = model.K.to_scipy(), model.M.to_scipy()
     mat_h = (K_h - SIGMA * M_h).tocsc()     # the caller's host inputs: K, M and the shifted matrix (thermal.py:288-290)
@@ -318,7 +484,6 @@ def run_ours(args, rank, world):
         vals[...] = A_h.data
         A_h.data = vals
     prob = model.prob
-
     Phib_h = D.pinned_empty((model.nnodes, N))
 
     def step_e2e():
@@ -331,7 +496,7 @@ def run_ours(args, rank, world):
         Phib = np.multiply.outer(vec_h, 2.0 * c / lam, out=Phib_h)     # written into page-locked memory
         lamb = -(c * c) / lam**2
         Phib[:, 0], lamb[0] = 0.0, 0.0
-        psi, data = s.solve_adjoint(Phib, method="sibk", rtol=1e-10, lanczos_guess=True)
+        psi, data = s.solve_adjoint(Phib, method="sibk", rtol=RTOL, lanczos_guess=True)
         dfdx = np.zeros(prob.nelems)
         s.add_total_derivative(lamb, Phib, psi, prob.dAdx, prob.dBdx, dfdx, adj_corr_data=data, deriv_type="tensor")
         return dfdx
@@ -351,11 +516,27 @@ def run_ours(args, rank, world):
         h2d, d2h = H.XFER["h2d"] // ke, H.XFER["d2h"] // ke
     clk = clocks.stop() if rank == 0 else None
     # ---- max over ranks ------------------------------------------------------------------------------
+    stage_keys = sorted(stage)
     if world > 1:
-        t = torch.tensor([ms, e2e_s or 0.0], dtype=torch.float64, device="cuda")
+        t = torch.tensor([ms, e2e_s or 0.0] + [stage[k] for k in stage_keys] + [coll["ms"] / max(args.steps, 1)],
+                         dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_s = float(t[0]), float(t[1])
-    units = world if designs else 1          # gradients produced per step by the whole job
+        ms, e2e_s = float(t[0]), float(t[1]) or None
+        stage = {k: float(v) for k, v in zip(stage_keys, t[2:2 + len(stage_keys)].tolist())}
+        coll["ms_per_step_max_over_ranks"] = float(t[-1])
+    # ---- the other configurations ------------------------------------------------------------------------
+    extras = {}
+    if not args.no_extras:
+        del flush
+        torch.cuda.empty_cache()
+        for name, fn in (("c3_buckling", lambda: run_c3(shard, rank, world, barrier)),
+                         ("c5_sweep", lambda: run_c5(rank, world, barrier, args.c5_designs))):
+            try:
+                extras[name] = fn()
+            except Exception as exc:                  # an extra leg must never cost the headline line
+                extras[name] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+                if world > 1:
+                    raise
     if rank != 0:
         return
     peaks = {}
@@ -364,8 +545,8 @@ def run_ours(args, rank, world):
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    # dominant kernel: the persistent triangular-solve kernel; headline = its single-RHS launches (the Lanczos
-    # recurrence), the multi-RHS launches of the adjoint solvers are listed beside it
+    # dominant kernel: the triangular solve; headline = its single-RHS launches (the Lanczos recurrence), the multi-RHS
+    # launches of the adjoint solvers are listed beside it
     fac = model.factor.lu
     by_rhs = {}
     tot_ms = 0.0
@@ -377,46 +558,74 @@ def run_ours(args, rank, world):
     kdom = max(solve_by_k, key=lambda k: solve_by_k[k][1]) if solve_by_k else 1
     dom = by_rhs.get(str(kdom), {"launches_per_step": 0, "ms_per_launch": 0.0, "algorithmic_bytes_per_launch": 0, "achieved_gbs": 0.0})
     achieved = dom["achieved_gbs"]
-    traffic = None
-    try:
-        ncu = json.load(open(os.path.join(ROOT, "profiles", "r1_solve_kernel_ncu.json")))
-        traffic = ncu.get("dram_bytes_per_launch", {}).get(str(kdom))
-    except Exception:
-        pass
-    line = base_line(args, ms / 1e3 / units, ms)
-    if strong is not None:
-        line["strong_single_gradient"] = strong
+    traffic, traffic_src = None, None
+    for cand in ("r2_solve_kernel_ncu.json", "r1_solve_kernel_ncu.json"):
+        try:
+            ncu = json.load(open(os.path.join(ROOT, "profiles", cand)))
+            traffic = ncu.get("dram_bytes_per_launch", {}).get(str(kdom))
+            traffic_src = "profiles/" + cand
+            break
+        except Exception:
+            continue
+    line = base_line(args, ms / 1e3, ms, world)
     line.update({
         "impl": "ours", "gpu_launches": int(launches // max(args.steps, 1)), "clocks": clk,
-        "e2e": {"value": (e2e_s / units) if e2e_s else e2e_s, "unit": "s", "h2d_bytes_per_step": int(h2d) * units,
-                "d2h_bytes_per_step": int(d2h) * units,
+        "e2e": {"value": e2e_s, "unit": "s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "note": "reference-facing numpy API: host scipy K, M, K - sigma*M (values; the shared int32 pattern is uploaded once "
-                        "per mesh) and host Phib (written by the host code each step) in page-locked host memory in; host lam, "
-                        "Phi, psi, dfdx out (numpy views of page-locked blocks); copies >= 1 MB go through a copy stream"},
-        "stages_s": stage, "per_step_ms": per_step_ms,
-        "roofline": {"bound": "hbm", "kernel": "multifrontal LDL^T triangular solve, forward + backward sweep, %d right-hand side(s): "
-                                               "subtree_kernel<%d> (forward, TMA-staged fronts) + solve_kernel<%d> (persistent cooperative "
-                                               "level phases) + subtree_kernel<%d> (backward); 'launch' below = one such solve call"
-                                               % (kdom, kdom, kdom, kdom),
+                        "per mesh, verified by a full comparison per matrix) and host Phib (written by the host code each step) in "
+                        "page-locked host memory in; host lam, Phi, psi, dfdx out (numpy views of page-locked blocks); Phi and Phib "
+                        "are uploaded again at every entry point (the host arrays are authoritative)"},
+        "stages_s": stage, "per_step_ms": per_step_ms, "parity": parity,
+        "roofline": {"bound": "hbm", "kernel": "multifrontal LDL^T triangular solve, forward + backward sweep, %d right-hand side(s); "
+                                               "'launch' below = one such solve call" % kdom,
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
-                     "traffic": traffic, "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"],
+                     "traffic": traffic, "traffic_source": traffic_src,
+                     "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"],
                      "launches_per_step": dom["launches_per_step"], "ms_per_launch": dom["ms_per_launch"],
                      "share_of_step": tot_ms / (ms * args.steps) if ms else None,
-                     "note": "issue/latency-bound, not DRAM-bound: 2 subtree phases (front mode) + 22 level phases separated by grid barriers "
-                             "(DESIGN.md section 5 has the ablation)",
                      "by_rhs": by_rhs},
         "timeline_ms_per_step": {k: v["ms"] / args.steps for k, v in tl.items()},
         "counts": {"eig_solves": model.profile["solve preconditioner count"],
                    "adjoint_solves": model.profile["adjoint preconditioner count"],
-                   "nnzL": model.symbolic[0].query("nnzL"), "n": model.nvars},
+                   "nnzL": model.symbolic[0].query("nnzL"), "n": model.nvars,
+                   "symbolic_s": model.profile.get("symbolic analysis time")},
     })
+    fp64 = fp64_tensor_roofline(model, tl, args.steps)
+    if fp64:
+        line["roofline_fp64_tensor"] = fp64
+    if coll is not None:
+        line["collectives_per_step"] = {"allgather_calls": coll["calls"] / max(args.steps, 1),
+                                        "allgather_bytes": coll["bytes"] / max(args.steps, 1),
+                                        "allgather_ms_max_over_ranks": coll.get("ms_per_step_max_over_ranks")}
+    line.update(extras)
     if world == 1 and not args.no_cpu_baseline:
-        ref = CpuReference(args.nx, N)
-        v = ref.step()
-        line["cpu_baseline"] = {"value": v, "unit": "s", "cores": 1, "kind": "port", "sample": ref.describe(),
-                                "detail": ref.last}
+        try:
+            ref = CpuGradient(args.nx, N, kind="port")
+            v = ref.step()
+            line["cpu_baseline"] = {"value": v, "unit": "s", "cores": host_threads(), "host_cpus": os.cpu_count(), "kind": "port",
+                                    "sample": ref.describe(1), "stages_s": ref.stages, "counts": ref.counts}
+        except Exception as exc:                      # pragma: no cover
+            line["cpu_baseline"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
     print(json.dumps(line))
+
+
+def fp64_tensor_roofline(model, tl, steps):
+    """Second roofline entry: the numeric LDL^T (frontal Schur-complement updates on the FP64 tensor pipe) against a DGEMM
+    peak measured live with the library's own DMMA micro-benchmark."""
+    try:
+        from eigd_b200 import device as D
+        peak = D.dmma_peak_tflops()
+        flops = model.symbolic[0].query("flops")
+        fms = tl.get("factor", {}).get("ms", 0.0) / max(tl.get("factor", {}).get("calls", 1), 1)
+        ach = flops / 1e12 / (fms / 1e3) if fms else None
+        return {"bound": "fp64_tensor", "kernel": "numeric multifrontal LDL^T (extend-add, pivot blocks, TRSM, DMMA trailing updates, "
+                "panel inverses): whole factorisation", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                "frac": (ach / peak) if (ach and peak) else None, "flops_per_launch": flops, "ms_per_launch": fms,
+                "peak_source": "eigd_dmma_peak: mma.sync.m8n8k4.f64 register-resident micro-benchmark, all SMs, measured in this run",
+                "traffic": None}
+    except Exception:
+        return None
 
 
 def main():

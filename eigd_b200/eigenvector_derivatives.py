@@ -58,8 +58,11 @@ def _check_symmetric_sampled(mat, nsample=64):
         less = (mid < hi) & (idx[np.minimum(mid, len(idx) - 1)] < j)
         lo, hi = np.where(less, mid + 1, lo), np.where(less, hi, mid)
     q = np.minimum(lo, len(idx) - 1)
-    scale = float(np.abs(v).max()) or 1.0
-    bad = (lo >= ptr[i + 1]) | (idx[q] != j) | (np.abs(val[q] - v) > 1e-10 * scale)
+    # assembled FE matrices are symmetric only up to the rounding of their COO sums (K + sigma G of
+    # examples/buckling.py differs by ~1e-10 of its largest entry across the diagonal): reject real asymmetry only
+    scale = max(float(np.abs(v).max()), float(np.abs(val[::97]).max())) or 1.0
+    found = (lo < ptr[i + 1]) & (idx[q] == j)          # scipy's sparse sums prune exact zeros: a missing mirror entry is 0.0
+    bad = np.abs(np.where(found, val[q], 0.0) - v) > 1e-6 * scale
     if bad.any():
         k = int(np.argmax(bad))
         raise ValueError("SpLuOperator: the matrix is not symmetric (entry (%d, %d)); the GPU factorisation is an "

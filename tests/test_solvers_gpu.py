@@ -335,22 +335,67 @@ def test_complex_operands_outside_basic_lanczos_raise(E, th):
         E.IRAM(N=4, m=20).solve(Ac, B, f, sigma)
 
 
-def test_adjoint_rhs_device_copy_is_reused_and_edits_are_seen(E, th, th_solver):
-    """solve_adjoint and add_total_derivative receive the same host Phib: one upload serves both; an in-place edit
-    between the calls (column scaling, the kind of edit callers make) is detected and uploaded again."""
+def test_host_arrays_are_authoritative_between_calls(E, th, th_solver):
+    """The caller owns Phib and the returned Phi (SURVEY.md 8b "Ownership"): ANY in-place edit between solve_adjoint
+    and add_total_derivative -- including a single entry in the middle of the array, which no sampled fingerprint
+    sees (round-1 advisor finding) -- must reach the device.  The reference examples do exactly that
+    (``Qb[node, i] += ...`` thermal.py:481, buckling.py:744; ``Q0[:, i] *= -1`` natural_frequency.py:383-390)."""
     s, f, lam, Phi = th_solver
+    n, N = Phi.shape
     Phib = np.array(th["Phib"], dtype=float)
-    d1 = s._phib_dev(Phib)
-    assert s._phib_dev(Phib) is d1                          # same array object, unchanged
-    assert np.array_equal(d1.cpu().numpy(), Phib)
-    same_values = Phib.copy()
-    d2 = s._phib_dev(same_values)                           # another object: uploaded
-    assert d2 is not d1 and np.array_equal(d2.cpu().numpy(), Phib)
-    same_values[:, 1] *= -2.0
-    d3 = s._phib_dev(same_values)
-    assert d3 is not d2 and np.array_equal(d3.cpu().numpy(), same_values)
-    # through the public calls: the gradient with a reused copy equals the gradient with a fresh solver-side upload
-    psi, data = s.solve_adjoint(Phib, method="sibk", rtol=1e-10)
-    r_shared = s.eval_adjoint_residual_norm(Phib, psi)
-    r_fresh = s.eval_adjoint_residual_norm(Phib.copy(), psi)
-    assert np.array_equal(np.asarray(r_shared[0]), np.asarray(r_fresh[0]))
+    lamb = np.array(th["lamb"], dtype=float)
+    A, B = th["A"], th["B"]
+    vec = np.random.default_rng(4).normal(size=n)
+    dAdx = lambda w, v: (w * v).sum(axis=-1) if w.ndim == 2 else w * v          # noqa: E731  any bilinear callback
+    dBdx = lambda w, v: ((w * v) * vec[:, None]).sum(axis=-1) if w.ndim == 2 else w * v * vec   # noqa: E731
+    psi, data = s.solve_adjoint(Phib, method="sibk", rtol=1e-12)
+    g0 = s.add_total_derivative(lamb, Phib, psi, dAdx, dBdx, np.zeros(n), adj_corr_data=data, deriv_type="tensor")
+    # (1) one entry in the middle of Phib, same array object
+    Phib[n // 2 + 3, 2] += 7.0
+    g1 = s.add_total_derivative(lamb, Phib, psi, dAdx, dBdx, np.zeros(n), adj_corr_data=data, deriv_type="tensor")
+    g1_fresh = s.add_total_derivative(lamb, Phib.copy(), psi, dAdx, dBdx, np.zeros(n), adj_corr_data=data, deriv_type="tensor")
+    assert np.array_equal(g1, g1_fresh) and not np.array_equal(g1, g0)
+    r1 = s.eval_adjoint_residual_norm(Phib, psi)[0]
+    assert np.array_equal(np.asarray(r1), np.asarray(s.eval_adjoint_residual_norm(Phib.copy(), psi)[0]))
+    Phib[n // 2 + 3, 2] -= 7.0
+    # (2) a sign flip of one column of the eigenvectors solve() returned, in place, through a slice view
+    Q = s.Phi[:, 1:]
+    Q[:, 1] *= -1.0
+    g2 = s.add_total_derivative(lamb, Phib, psi, dAdx, dBdx, np.zeros(n), adj_corr_data=data, deriv_type="tensor")
+    assert not np.array_equal(g2, g0)
+    Q[:, 1] *= -1.0
+    g3 = s.add_total_derivative(lamb, Phib, psi, dAdx, dBdx, np.zeros(n), adj_corr_data=data, deriv_type="tensor")
+    assert np.array_equal(g3, g0)
+    # (3) one entry in the middle of Phi
+    s.Phi[n // 2, 3] += 0.5
+    g4 = s.add_total_derivative(lamb, Phib, psi, dAdx, dBdx, np.zeros(n), adj_corr_data=data, deriv_type="tensor")
+    assert not np.array_equal(g4, g0)
+    s.Phi[n // 2, 3] -= 0.5
+
+
+def test_pattern_cache_full_compare_and_ids(E):
+    """The CSR pattern cache never trusts a sampled fingerprint or array identity: an in-place edit of one column index
+    in the middle of the array gives a different entry; ids are not recycled."""
+    import scipy.sparse as sp
+    from eigd_b200 import device as D
+    n = 400
+    A = (sp.random(n, n, 0.02, random_state=1, format="csr") + sp.eye(n)).tocsr()
+    A.sort_indices()
+    c1 = D.CsrDevice.from_scipy(A)
+    c2 = D.CsrDevice.from_scipy(A)
+    assert c1.pattern_id == c2.pattern_id and c2.uploaded_bytes == A.nnz * 8
+    row = n // 2
+    p = A.indptr[row] + 1
+    if A.indptr[row + 1] - A.indptr[row] >= 3 and A.indices[p + 1] - A.indices[p - 1] > 2:
+        A.indices[p] = A.indices[p - 1] + 1 if A.indices[p] != A.indices[p - 1] + 1 else A.indices[p] + 1
+    else:
+        A = A.copy()
+        A.indices[-1] = A.indices[-1] - 1 if A.indices[-1] - 1 > (A.indices[-2] if A.indptr[-2] < A.nnz - 1 else -1) else A.indices[-1]
+    c3 = D.CsrDevice.from_scipy(A)
+    if not np.array_equal(c3.indices.cpu().numpy(), c1.indices.cpu().numpy()):
+        assert c3.pattern_id != c1.pattern_id
+    ids = set()
+    for k in range(40):                                     # many dead patterns of equal size: ids stay unique
+        M = sp.random(50, 50, 0.1, random_state=k, format="csr") + sp.eye(50)
+        ids.add(D.CsrDevice.from_scipy(M.tocsr()).pattern_id)
+    assert len(ids) >= 39
