@@ -49,9 +49,13 @@ SIGNATURES = {
     "eigd_solve_timing_begin": (c_int, []),
     "eigd_solve_timing_end": (c_int, [c_ptr, c_ptr]),
     "eigd_solve_set_phase_times": (c_int, [c_ptr]),
+    "eigd_solve_set_trace": (c_int, [c_ptr]),
     "eigd_solve_num_phases": (c_int, [c_ptr]),
     "eigd_lanczos_extend": (c_int, [c_ptr, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_int,
                                     c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_ptr]),
+    "eigd_block_lanczos_extend": (c_int, [c_ptr, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64,
+                                          c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "eigd_block_lanczos_start": (c_int, [c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_ptr]),
     "eigd_q4_assemble": (c_int, [c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_ptr]),
     "eigd_q4_quadforms": (c_int, [c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_ptr, c_ptr, c_dbl, c_dbl, c_ptr]),
     "eigd_q4_material": (c_int, [c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),

@@ -178,8 +178,136 @@ def lanczos_thick_restart(Bip, factor, k, ncv, sigma, mode="normal", tol=0.0, ma
     return st
 
 
+BLOCK_SIZE = int(__import__("os").environ.get("EIGD_LANCZOS_BLOCK", "2"))
+
+
+def lanczos_block_thick_restart(Bip, factor, k, ncv, sigma, P, mode="normal", tol=0.0, maxiter=None, v0=None, seed=None):
+    """Block thick-restart Lanczos (block size P) on OP = factor o Bip in the Bip inner product; returns LanczosState.
+
+    Same contract as ``lanczos_thick_restart`` (Vt: ncv B-orthonormal rows, T = V^T B OP V, Z = V Y[:, sel]); T is block
+    tridiagonal with P x P blocks plus the restart arrow.  One native call per restart cycle (csrc/block_krylov.cu),
+    one device -> host copy of the cycle's P x P blocks; the ncv x ncv ``eigh`` runs on the host as in the reference
+    (eigd/eigenvector_derivatives.py:1958).  P right-hand sides per triangular solve cost little more than one on
+    this hardware, and the number of operator applications stays about the same, so the eigensolve needs about 1/P of
+    the sequential solves of the single-vector recurrence."""
+    n = Bip.shape[0]
+    if maxiter is None:
+        maxiter = 10 * n
+    eps = np.finfo(np.float64).eps
+    if tol <= 0.0:
+        tol = eps
+    eps23 = eps ** (2.0 / 3.0)
+    Vt = D.empty(ncv + P, n)
+    BVt = D.empty(ncv + P, n)
+    tmp = D.empty(ncv, n)
+    nstep_max = (ncv + P - 1) // P + 1
+    blocks = D.zeros(2, nstep_max, P, P)          # [0]: diagonal blocks A_j, [1]: sub-diagonal blocks R_j of the cycle
+    H1, H2 = D.zeros((ncv + P) * P), D.zeros((ncv + P) * P)
+    scratch = D.zeros(3 * P * P)
+    st = LanczosState()
+    # start block: P vectors forced into the range of OP (as ARPACK's dgetv0 does for its one vector)
+    if v0 is not None:
+        w0 = np.asarray(to_host(v0) if is_dev(v0) else v0, dtype=float).reshape(n)
+        rest = np.random.default_rng(0 if seed is None else seed).uniform(-1.0, 1.0, (P - 1, n))
+        W0 = to_dev(np.vstack([w0[None, :], rest]))
+    elif seed is None:
+        W0 = to_dev(np.random.default_rng().uniform(-1.0, 1.0, (P, n)))
+    else:
+        key = (int(seed), int(n), int(P), str(D.dev()))
+        W0 = _SEEDED_V0.get(key)
+        if W0 is None:
+            if len(_SEEDED_V0) >= 4:
+                _SEEDED_V0.clear()
+            W0 = _SEEDED_V0[key] = to_dev(np.random.default_rng(seed).uniform(-1.0, 1.0, (P, n)))
+    BW0 = Bip.spmm(W0.T)                                    # (n, P) row-major
+    factor.solve_dev(BW0, out=Vt[:P].T)
+    st.nops += P
+    D.block_lanczos_start(Bip, Vt, BVt, P, scratch)
+    T = np.zeros((ncv + P, ncv + P))
+    if ncv % P:
+        raise ValueError("block Lanczos needs ncv to be a multiple of the block size")
+    j0, m0 = 0, P
+    ncv_c = ncv
+    best, stagnant = np.inf, 0
+    while True:
+        nsteps = (ncv_c - j0) // P
+        D.block_lanczos_extend(factor, Bip, Vt, BVt, P, j0, m0, ncv_c, blocks[0], blocks[1], H1, H2, scratch)
+        st.nops += ncv_c - j0
+        st.ncycles += 1
+        blk = to_host(blocks[:, :nsteps])                   # the one D2H of the cycle
+        if not np.all(np.isfinite(blk)):
+            raise ArpackError("Lanczos breakdown: rank-deficient Krylov block or non-positive B-norm (is B positive "
+                              "definite and the shifted matrix non-singular?)")
+        for s_ in range(nsteps):
+            j, m = j0 + s_ * P, m0 + s_ * P
+            A_j, R_j = blk[0, s_], blk[1, s_]
+            T[j:j + P, j:j + P] = 0.5 * (A_j + A_j.T)
+            T[m:m + P, j:j + P] = R_j
+            T[j:j + P, m:m + P] = R_j.T
+        Tm = T[:ncv_c, :ncv_c]
+        R_last = T[ncv_c:ncv_c + P, ncv_c - P:ncv_c]
+        theta, Y = np.linalg.eigh(Tm)
+        order = np.argsort(-np.abs(theta))                  # which = "LM"
+        bounds = np.linalg.norm(R_last @ Y[ncv_c - P:ncv_c, :], axis=0)
+        wanted = order[:k]
+        relb = bounds[wanted] / np.maximum(eps23, np.abs(theta[wanted]))
+        conv = relb <= tol
+        nconv = int(conv.sum())
+        worst = float(relb.max())
+        if worst < 0.5 * best:
+            best, stagnant = worst, 0
+        else:
+            stagnant += 1
+        # the estimates of a block recurrence bottom out at a few tens of eps * |theta| (rounding of the P x P block
+        # factorisations): accept there instead of iterating on noise
+        done = nconv == k or worst <= 64.0 * eps
+        if done or st.nops >= maxiter or ncv_c >= n:
+            break
+        # ---- thick restart: keep the wanted Ritz vectors plus a share of the converged count; the kept count leaves
+        # a whole number of blocks for the next cycle
+        kk = max(min(k + min(nconv, (ncv - k) // 2), ncv - 2 * P), 1)
+        kk += (ncv - kk) % P                                # ... so that the next cycle ends exactly at ncv
+        if kk > ncv - P:
+            kk -= P
+        keep = order[:kk]
+        Yk = small_to_dev(Y[:, keep])
+        D.gemm_nn(Vt[:ncv_c].T, Yk, tmp[:kk].T, alpha=1.0, beta=0.0)
+        res_V = Vt[ncv_c:ncv_c + P].clone()
+        Vt[:kk].copy_(tmp[:kk])
+        D.gemm_nn(BVt[:ncv_c].T, Yk, tmp[:kk].T, alpha=1.0, beta=0.0)
+        res_BV = BVt[ncv_c:ncv_c + P].clone()
+        BVt[:kk].copy_(tmp[:kk])
+        Vt[kk:kk + P].copy_(res_V)
+        BVt[kk:kk + P].copy_(res_BV)
+        S = R_last @ Y[ncv_c - P:ncv_c, keep]               # P x kk coupling of the residual block to the kept Ritz vectors
+        T[:, :] = 0.0
+        T[np.arange(kk), np.arange(kk)] = theta[keep]
+        T[kk:kk + P, :kk] = S
+        T[:kk, kk:kk + P] = S.T
+        j0, m0 = kk, kk + P
+
+    if nconv < k and not done:
+        lam = _theta_to_lambda(theta[wanted][conv], sigma, mode)
+        raise ArpackNoConvergence("ARPACK error -1: No convergence (%d iterations, %d/%d eigenvectors converged)"
+                                  % (st.nops, nconv, k), lam, None)
+    lam = _theta_to_lambda(theta[wanted], sigma, mode)
+    srt = np.argsort(lam)
+    sel = wanted[srt]
+    st.d = lam[srt]
+    st.theta = theta[sel]
+    st.resid = bounds[sel]
+    st.T = Tm.copy()
+    st.eigh_T = (theta.copy(), Y.copy())
+    st.sel = sel.copy()
+    st.Vt = Vt[:ncv_c]
+    Z = D.empty(n, k)
+    D.gemm_nn(st.Vt.T, small_to_dev(Y[:, sel]), Z, alpha=1.0, beta=0.0)
+    st.Z = Z
+    return st
+
+
 def eigsh_mod(A, k=6, M=None, sigma=None, which="LM", v0=None, ncv=None, maxiter=None, tol=0,
-              return_eigenvectors=True, Minv=None, OPinv=None, mode="normal", return_state=False, seed=None):
+              return_eigenvectors=True, Minv=None, OPinv=None, mode="normal", return_state=False, seed=None, block=None):
     """Signature of reference eigd/arpack.py:104-118 (scipy's eigsh plus the 4-tuple return).
 
     A : for mode="normal" unused beyond its shape; for mode="buckling" the matrix ARPACK
@@ -216,7 +344,14 @@ def eigsh_mod(A, k=6, M=None, sigma=None, which="LM", v0=None, ncv=None, maxiter
         ncv = min(n, max(2 * k + 1, 20))
     if ncv > n or ncv <= k:
         raise ValueError("ncv must be k<ncv<=n")
-    st = lanczos_thick_restart(Bip, OPinv, k, ncv, float(sigma), mode=mode, tol=float(tol), maxiter=maxiter, v0=v0, seed=seed)
+    P = BLOCK_SIZE if block is None else int(block)
+    while P > 1 and (P > 4 or ncv % P or ncv - k < 3 * P or ncv + P > 128 or n < ncv + P):
+        P -= 1                        # the basis must hold a whole number of blocks (and a few of them): else smaller blocks
+    if P > 1:
+        st = lanczos_block_thick_restart(Bip, OPinv, k, ncv, float(sigma), P, mode=mode, tol=float(tol), maxiter=maxiter,
+                                         v0=v0, seed=seed)
+    else:
+        st = lanczos_thick_restart(Bip, OPinv, k, ncv, float(sigma), mode=mode, tol=float(tol), maxiter=maxiter, v0=v0, seed=seed)
     if not return_eigenvectors:
         return st.d
     if return_state:                  # the caller keeps the basis and the eigenvectors in HBM (IRAM.solve)

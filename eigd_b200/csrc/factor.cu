@@ -646,7 +646,7 @@ static void factor_layout(const eigd_symbolic* s, const SymDevHolder* h, int max
   sz[10] = align256((int64_t)s->n * kc * 8);           // xperm
   sz[11] = 256;                                        // amax
   sz[12] = 256;                                        // info
-  sz[13] = 256;                                        // barrier
+  sz[13] = align256(256 + (int64_t)s->nsuper * 8);     // grid-barrier counter (first 256 bytes) + completion counters of the solve
   sz[14] = align256((int64_t)s->n * kc * 8);           // bperm
   sz[15] = 0;
 }
@@ -702,12 +702,14 @@ extern "C" int eigd_factor_create_in(eigd_symbolic* s, int max_rhs, void* d_work
   f->xperm = (double*)p; p += sz[10];
   f->amax = (unsigned long long*)p; p += sz[11];
   f->info = (unsigned long long*)p; p += sz[12];
-  f->barrier = (unsigned long long*)p; p += sz[13];
+  f->barrier = (unsigned long long*)p;
+  f->cnt = (unsigned*)(p + 256); p += sz[13];
+  f->epoch = 0;
   f->bperm = (double*)p;
   f->bar_base = 0;
   // slab rows that no child writes must read as zero for ever; the written ones are rewritten by every solve
   cudaError_t eb = cudaMemsetAsync(f->wbuf, 0, (size_t)sz[8], g_eigd_stream);
-  if (eb == cudaSuccess) eb = cudaMemsetAsync(f->barrier, 0, 256, g_eigd_stream);
+  if (eb == cudaSuccess) eb = cudaMemsetAsync(f->barrier, 0, (size_t)sz[13], g_eigd_stream);
   if (eb != cudaSuccess) { eigd_set_error("factor_create: memset -> %s", cudaGetErrorString(eb)); eigd_factor_destroy(f); return 100 + (int)eb; }
   *out = f;
   return 0;

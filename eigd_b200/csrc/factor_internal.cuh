@@ -38,6 +38,8 @@ struct Launch {
 // device copy of the solve plan (solve_plan.hpp)
 struct SolvePlanDev {
   TileRec* tiles = nullptr;
+  TileDep* deps = nullptr;      // parallel to tiles
+  int* dep_ovf = nullptr;
   PhaseRec* phases = nullptr;
   int* ovf_row = nullptr;
   int* ovf = nullptr;
@@ -78,6 +80,8 @@ struct eigd_factor {
   unsigned long long* info = nullptr;   // 4 values
   unsigned long long* barrier = nullptr;  // arrival counter of the grid barrier (monotone)
   unsigned long long bar_base = 0;        // arrivals issued so far (host mirror)
+  unsigned* cnt = nullptr;                // per-front completion counters of the solve (2 per supernode), monotone
+  unsigned epoch = 0;                     // cooperative solve launches issued so far (host mirror)
   double piv_tol = 1e-11;
   int64_t bytes = 0;
   char* base = nullptr;

@@ -8,7 +8,11 @@
 //     forward :  [y1 ; u2] = S w1,   z1 = D^{-1} y1 kept, u2 (+ gathered child rows) passed up;
 //     backward:  x1 = S^T [z1 ; x2], x2 = solution entries of the front's below rows (ancestors).
 // Neither sweep has a dependency inside a front, so a level of the assembly tree is one batch of
-// independent dense products: the kernel walks 2 * nlevels phases separated by grid barriers.
+// independent dense products.  Above the cut the persistent kernel walks the 2 * nlevels level phases in order,
+// but there is NO grid barrier between them: every front owns a forward and a backward completion counter, a tile
+// waits (ld.acquire spin of one lane per dependency) only for the fronts it actually reads from -- its children
+// in the forward sweep, its parent in the backward sweep -- and the panel entries of its first chunk are already
+// in flight while it waits (TileDep in solve_plan.hpp).
 //
 // Mapping.  512-thread CTAs, one (or two) per SM, cooperative launch.  A warp tile is 32 consecutive
 // outputs of one front (lane = output), the reduction dimension is streamed in chunks of 32 whose
@@ -58,13 +62,19 @@ struct SolveArgs {
   double* X;
   int64_t xrs, xcs;
   int n, k;
-  unsigned long long* barrier;
+  const TileDep* deps;            // per-tile completion-counter dependencies (level phases)
+  const int* dep_ovf;
+  unsigned long long* barrier;    // arrival counter of the (rare) grid barriers, monotone
   unsigned long long bar_base;
+  unsigned* cnt;                  // completion counters: 2 * supernode + direction, monotone over the solves of a factor
+  unsigned epoch;                 // number of this solve (1, 2, ...): counter c is complete at epoch * tiles(c)
   int dbg;                        // developer ablation (EIGD_SOLVE_DBG): bit 0 no operand loads, bit 1 no panel copies, bit 2 no stores
   int p_begin, p_end;             // phases run by the cooperative kernel
   int ring_w;                     // bytes of shared-memory panel buffer per warp (front mode of the subtree phases)
   int rec_cap;                    // tile records of a slot that fit in shared memory
   unsigned long long* times;      // developer profiling: %globaltimer of CTA 0 after every phase (NULL: off)
+  long long* trace;               // developer profiling: clock64 of CTA 0 / warp 0 inside its first tile of every level
+                                  // phase, 8 slots per phase: start, waited, product done, reduced, stored, signalled
 };
 
 // vectors produced earlier in the same launch by other SMs are read through L2 (ld.global.cg): L1 is
@@ -142,9 +152,44 @@ struct DefaultMC {
   static constexpr int value = KT <= 2 ? 32 : (KT <= 10 ? 16 : 8);
 };
 
-template <int KT, int MC, class StageFn>
+// Completion-counter wait of one tile: lane d < 2 polls inline dependency d, further dependencies are polled
+// lane-strided from the overflow list; the warp leaves together.  Called at most once per tile (first use).
+struct DepWait {
+  const unsigned* cnt;
+  const int* ovf;
+  unsigned epoch;
+  TileDep td;
+  bool pending;
+  __device__ __forceinline__ static void spin(const unsigned* c, unsigned need) {
+    unsigned v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(c) : "memory");
+    } while ((int)(v - need) < 0);
+  }
+  __device__ __forceinline__ void operator()(int lane) {
+    if (!pending) return;
+    pending = false;
+    if (lane < 2 && lane < td.ndep) spin(cnt + (lane ? td.d1 : td.d0), epoch * (unsigned)(lane ? td.n1 : td.n0));
+    for (int q = 2 + lane; q < td.ndep; q += 32) {
+      const int* e = ovf + td.ovf + 2 * (q - 2);
+      spin(cnt + __ldg(e), epoch * (unsigned)__ldg(e + 1));
+    }
+    __syncwarp();
+  }
+};
+struct NoWait {
+  __device__ __forceinline__ void operator()(int) {}
+};
+
+__device__ __forceinline__ void signal_done(unsigned* c) {
+  // the warp's stores happen-before lane 0's release through the warp barrier (cumulativity)
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(c) : "memory");
+}
+
+template <int KT, int MC, class StageFn, class WaitFn>
 __device__ __forceinline__ void warp_panel_product(const double* __restrict__ M, int64_t ld, int c0, int c1, int lane,
-                                                   double* stage, double* acc, StageFn stage_fn) {
+                                                   double* stage, double* acc, StageFn stage_fn, WaitFn& wait) {
   constexpr int g = 0, nks = 1;
   for (int cc = c0; cc < c1; cc += 32) {
     const int ncol = min(32, c1 - cc);
@@ -156,6 +201,7 @@ __device__ __forceinline__ void warp_panel_product(const double* __restrict__ M,
     double v[KT];
 #pragma unroll
     for (int r = 0; r < KT; ++r) v[r] = 0.0;
+    wait(lane);                     // the panel loads above are in flight while the producers of the operands finish
     if (lane < ncol) stage_fn(cc + lane, v);
 #pragma unroll
     for (int r = 0; r < KT; ++r) stage[r * 32 + lane] = v[r];
@@ -178,6 +224,8 @@ __device__ __forceinline__ void warp_panel_product(const double* __restrict__ M,
   }
 }
 
+// Grid-wide barrier, only for the rare in-kernel phases that are not synchronised by completion counters (a subtree
+// phase executed inside the cooperative kernel, the in-kernel copy of the permuted right-hand side).
 __device__ __forceinline__ void grid_barrier(unsigned long long* ctr, unsigned long long target) {
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -189,13 +237,16 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* ctr, unsigned l
   }
   __syncthreads();
 }
+__host__ __device__ inline bool barrier_between(const PhaseRec& a, const PhaseRec& b, int p) {
+  return a.ws == 0 || b.ws == 0 || p == 0;
+}
 
 // the products of one warp tile: slice `slice` of `ws` of the reduction dimension.
 // use_perm: the right-hand side is gathered from B through perm (first phase; later phases read the
 // permuted copy written during the first one)
-template <int KT, int MC = DefaultMC<KT>::value>
+template <int KT, int MC = DefaultMC<KT>::value, class WaitFn>
 __device__ __forceinline__ void tile_compute(const SolveArgs& a, int dir, bool use_perm, const TileRec& tr, int lane,
-                                             int slice, int ws, double* stage, double* acc) {
+                                             int slice, int ws, double* stage, double* acc, WaitFn& wait) {
   constexpr int to = SOLVE_TILE;
   const int k = a.k;
   const int nc = tr.nc, f = tr.nc + tr.nb;
@@ -203,7 +254,6 @@ __device__ __forceinline__ void tile_compute(const SolveArgs& a, int dir, bool u
   const int out = o0 + (lane % to);
   if (dir == 0) {
     // ---- forward: outputs are front rows; acc = S[row, 0:cend) w1 (+ the children's updates of the row)
-    if (slice == 0 && lane < to && out >= nc && out < f) child_add<KT>(a, tr.w_off + out, tr.link, acc);
     const int cend = min(nc, o0 + to);                  // S is lower triangular inside the pivot rows
     const int per = (cend + ws - 1) / ws;
     const int c0 = slice * per, c1 = min(cend, c0 + per);
@@ -219,7 +269,16 @@ __device__ __forceinline__ void tile_compute(const SolveArgs& a, int dir, bool u
         add_row<KT>(a.bperm, tr.first + c, k, v);
       }
       child_add<KT>(a, tr.w_off + c, tr.link, v);
-    });
+    }, wait);
+    wait(lane);
+    if (slice == 0 && lane < to && out >= nc && out < f) {
+      double cu[KT];                                    // the children's updates of this output row
+#pragma unroll
+      for (int r = 0; r < KT; ++r) cu[r] = 0.0;
+      child_add<KT>(a, tr.w_off + out, tr.link, cu);
+#pragma unroll
+      for (int r = 0; r < KT; ++r) acc[r] += cu[r];
+    }
   } else {
     // ---- backward: outputs are pivot columns; acc = S^T[col, o0:f) [z1 ; x2]
     const int len = f - o0;
@@ -229,7 +288,8 @@ __device__ __forceinline__ void tile_compute(const SolveArgs& a, int dir, bool u
     warp_panel_product<KT, MC>(M, nc, i0, i1, lane, stage, acc, [&](int i, double* v) {
       if (i < nc) add_row<KT>(a.ybuf, tr.first + i, k, v);
       else add_row<KT>(a.xperm, __ldg(&a.sn_rows[tr.row_off + i - nc]), k, v);
-    });
+    }, wait);
+    wait(lane);
   }
 }
 
@@ -611,7 +671,8 @@ __device__ __forceinline__ void fronts_phase(const SolveArgs& a, int dir, bool u
           double acc[KT];
 #pragma unroll
           for (int r = 0; r < KT; ++r) acc[r] = 0.0;
-          tile_compute<KT, (KT <= 2 ? 8 : DefaultMC<KT>::value)>(a, dir, use_perm, tr, lane, 0, 1, stage, acc);
+          NoWait nw;
+          tile_compute<KT, (KT <= 2 ? 8 : DefaultMC<KT>::value)>(a, dir, use_perm, tr, lane, 0, 1, stage, acc, nw);
           tile_store<KT>(a, dir, tr, lane, acc);
         }
       } else {
@@ -687,12 +748,16 @@ __global__ void __launch_bounds__(NW * 32, 1) subtree_kernel(SolveArgs a, int p)
   }
 }
 
-// The phases [a.p_begin, a.p_end) as one persistent cooperative kernel, a grid barrier between consecutive phases.
+// The phases [a.p_begin, a.p_end) as one persistent cooperative kernel.  Level phases follow each other WITHOUT a
+// grid barrier: tiles are handed out in a fixed global order (phase by phase, CTA-strided inside a phase), every CTA
+// walks its share in that order, and a tile spins only on the completion counters of the fronts it reads from
+// (TileDep).  A dependency always lies earlier in the global order and all CTAs are co-resident (cooperative
+// launch), so the earliest unfinished tile can always run: no deadlock.
 template <int KT>
 __global__ void __launch_bounds__(SOLVE_WARPS * 32, 1) solve_kernel(SolveArgs a) {
   extern __shared__ double smem[];
   __shared__ PhaseRec s_phase[MAX_PHASES_SMEM];
-  __shared__ int4 s_next[SOLVE_WARPS][3];                  // first tile record of the next phase, per warp
+  __shared__ int4 s_next[SOLVE_WARPS][5];                  // first tile record + dependencies of the next phase, per warp
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double* stage = smem + warp * (32 * KT);                 // [KT][32] per warp
   double* part = smem + SOLVE_WARPS * 32 * KT;             // [SOLVE_WARPS][KT][32] partial sums
@@ -716,15 +781,17 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32, 1) solve_kernel(SolveArgs a)
     const bool use_perm = (p == 0);
     // request this warp's first tile record of the NEXT phase now (static schedule): the load completes
     // behind this phase's work instead of in front of the next phase's
-    bool nxt_have = false;
+    bool nxt_have = false, bar_after = false;
     int4 nxt = make_int4(0, 0, 0, 0);
     if (p + 1 < a.p_end) {
       const PhaseRec nx = (p + 1) < MAX_PHASES_SMEM ? s_phase[p + 1] : a.phases[p + 1];
+      bar_after = barrier_between(ph, nx, p);
       if (nx.ws > 0) {
         const int te = (int)blockIdx.x * (SOLVE_WARPS / nx.ws) + warp / nx.ws;
         if (te < nx.ntiles) {
           nxt_have = true;
           if (lane < 3) nxt = __ldg(reinterpret_cast<const int4*>(a.tiles + nx.tile_off + te) + lane);
+          else if (lane < 5) nxt = __ldg(reinterpret_cast<const int4*>(a.deps + nx.tile_off + te) + (lane - 3));
         }
       }
     }
@@ -750,7 +817,8 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32, 1) solve_kernel(SolveArgs a)
             double acc[KT];
 #pragma unroll
             for (int r = 0; r < KT; ++r) acc[r] = 0.0;
-            tile_compute<KT>(a, dir, use_perm, tr, lane, 0, 1, stage, acc);
+            NoWait nw;
+            tile_compute<KT>(a, dir, use_perm, tr, lane, 0, 1, stage, acc, nw);
             tile_store<KT>(a, dir, tr, lane, acc);
           }
           __syncthreads();      // CTA-scope ordering: the level's results are visible to the whole slot
@@ -769,10 +837,35 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32, 1) solve_kernel(SolveArgs a)
         TileRec tr;
         tr.first = tr.nc = tr.nb = tr.tile = 0;
         tr.soff = tr.w_off = tr.row_off = tr.link = 0;
+        DepWait dw;
+        dw.cnt = a.cnt;
+        dw.ovf = a.dep_ovf;
+        dw.epoch = a.epoch;
+        dw.pending = false;
+        dw.td.self = 0;
         if (have) {
-          if (have_next && ct == (int)blockIdx.x) tr = unpack_tile(s_next[warp][0], s_next[warp][1], s_next[warp][2]);
-          else tr = load_tile(a.tiles + tile_off + te);
-          tile_compute<KT>(a, dir, use_perm, tr, lane, slice, ws, stage, acc);
+          int4 d0, d1;
+          if (have_next && ct == (int)blockIdx.x) {
+            tr = unpack_tile(s_next[warp][0], s_next[warp][1], s_next[warp][2]);
+            d0 = s_next[warp][3];
+            d1 = s_next[warp][4];
+          } else {
+            tr = load_tile(a.tiles + tile_off + te);
+            const int4* q = reinterpret_cast<const int4*>(a.deps + tile_off + te);
+            d0 = __ldg(q);
+            d1 = __ldg(q + 1);
+          }
+          dw.td.self = d0.x; dw.td.ndep = d0.y; dw.td.d0 = d0.z; dw.td.n0 = d0.w;
+          dw.td.d1 = d1.x; dw.td.n1 = d1.y; dw.td.ovf = d1.z; dw.td.pad = 0;
+          dw.pending = dw.td.ndep > 0;
+          const bool tr_on = a.trace && blockIdx.x == 0 && ct == 0 && threadIdx.x == 0;
+          if (tr_on) a.trace[8 * p + 0] = clock64();
+          if (a.trace) {              // trace build of the chain: wait first so that the segments separate
+            dw(lane);
+            if (tr_on) a.trace[8 * p + 1] = clock64();
+          }
+          tile_compute<KT>(a, dir, use_perm, tr, lane, slice, ws, stage, acc, dw);
+          if (tr_on) a.trace[8 * p + 2] = clock64();
         }
         if (ws > 1) {
 #pragma unroll
@@ -783,16 +876,25 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32, 1) solve_kernel(SolveArgs a)
 #pragma unroll
               for (int r = 0; r < KT; ++r) acc[r] += part[((warp + s) * KT + r) * 32 + lane];
         }
-        if (have && slice == 0) tile_store<KT>(a, dir, tr, lane, acc);
+        const bool tr_on2 = a.trace && blockIdx.x == 0 && ct == 0 && threadIdx.x == 0;
+        if (tr_on2) a.trace[8 * p + 3] = clock64();
+        if (have && slice == 0) {
+          tile_store<KT>(a, dir, tr, lane, acc);
+          if (tr_on2) a.trace[8 * p + 4] = clock64();
+          signal_done(a.cnt + dw.td.self);
+          if (tr_on2) a.trace[8 * p + 5] = clock64();
+        }
         if (ws > 1) __syncthreads();
       }
     }
     // ---- hand the prefetched first tile record of the next phase to the whole warp
     have_next = nxt_have;
-    if (nxt_have && lane < 3) s_next[warp][lane] = nxt;
+    if (nxt_have && lane < 5) s_next[warp][lane] = nxt;
     __syncwarp();
-    target += gridDim.x;
-    if (p + 1 < a.p_end) grid_barrier(a.barrier, target);
+    if (bar_after) {
+      target += gridDim.x;
+      grid_barrier(a.barrier, target);
+    }
     if (a.times && blockIdx.x == 0 && threadIdx.x == 0) {
       unsigned long long t;
       asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -865,6 +967,9 @@ int launch_solve(int slot, eigd_factor* f, SolveArgs& a) {
   const std::vector<PhaseRec>& hp = f->h->solve.host_phases;
   const int np = a.nphases;
   a.barrier = f->barrier;
+  a.cnt = f->cnt;
+  a.deps = f->h->solve.deps;
+  a.dep_ovf = f->h->solve.dep_ovf;
   a.ring_w = c.ring_w;
   a.rec_cap = c.rec_cap;
   // subtree phases in front mode run as their own launches in front of / behind the cooperative level kernel
@@ -873,17 +978,21 @@ int launch_solve(int slot, eigd_factor* f, SolveArgs& a) {
   a.p_begin = sub_first ? 1 : 0;
   a.p_end = sub_last ? np - 1 : np;
   a.bar_base = f->bar_base;
+  a.epoch = 0;
   if (sub_first) {
     subtree_kernel<KT, SubCfg<KT>::NW, SubCfg<KT>::PIPE><<<hp[0].level, SubCfg<KT>::NW * 32, c.smem_sub, g_eigd_stream>>>(a, 0);
     EIGD_CUDA(cudaGetLastError());
     ++g_eigd_launches;
   }
   if (a.p_end > a.p_begin) {
+    a.epoch = ++f->epoch;            // one epoch per cooperative launch: the completion counters never reset
+    int nbar = 0;
+    for (int p = a.p_begin; p + 1 < a.p_end; ++p) nbar += barrier_between(hp[p], hp[p + 1], p) ? 1 : 0;
     void* params[] = {(void*)&a};
     EIGD_CUDA(cudaLaunchCooperativeKernel((void*)solve_kernel<KT>, dim3(c.grid), dim3(SOLVE_WARPS * 32), params, c.smem,
                                           g_eigd_stream));
     ++g_eigd_launches;
-    f->bar_base += (unsigned long long)(a.p_end - a.p_begin - 1) * (unsigned long long)c.grid;
+    f->bar_base += (unsigned long long)nbar * (unsigned long long)c.grid;
   }
   if (sub_last) {
     subtree_kernel<KT, SubCfg<KT>::NW, SubCfg<KT>::PIPE><<<hp[np - 1].level, SubCfg<KT>::NW * 32, c.smem_sub, g_eigd_stream>>>(a,
@@ -907,6 +1016,8 @@ int build_solve_plan_dev(eigd_symbolic* S, SymDevHolder* h) {
   SolvePlanDev& d = h->solve;
   int rc = 0;
   rc |= upload_vec(h, P.tiles, &d.tiles);
+  rc |= upload_vec(h, P.deps, &d.deps);
+  rc |= upload_vec(h, P.dep_ovf, &d.dep_ovf);
   rc |= upload_vec(h, P.phases, &d.phases);
   rc |= upload_vec(h, P.ovf_row, &d.ovf_row);
   rc |= upload_vec(h, P.ovf, &d.ovf);
@@ -953,7 +1064,10 @@ extern "C" int eigd_solve_timing_end(int64_t* calls_by_k, double* ms_by_k) {
 
 // developer profiling hook: device buffer of (nphases + 1) u64 receiving per-phase timestamps of the next solves
 static unsigned long long* g_phase_times = nullptr;
+static long long* g_trace = nullptr;
 extern "C" int eigd_solve_set_phase_times(void* d_buf) { g_phase_times = (unsigned long long*)d_buf; return 0; }
+// developer profiling: device buffer of 8 * nphases i64 (see SolveArgs::trace)
+extern "C" int eigd_solve_set_trace(void* d_buf) { g_trace = (long long*)d_buf; return 0; }
 extern "C" int eigd_solve_num_phases(const eigd_factor* f) { return f->h->solve.nphases; }
 
 extern "C" int eigd_factor_solve(eigd_factor* f, const double* B, int64_t brs, int64_t bcs, double* X, int64_t xrs,
@@ -994,6 +1108,7 @@ extern "C" int eigd_factor_solve(eigd_factor* f, const double* B, int64_t brs, i
     a.xcs = xcs;
     a.k = kc;
     a.times = g_phase_times;
+    a.trace = g_trace;
     {
       static int dbg = -1;
       if (dbg < 0) { const char* e = getenv("EIGD_SOLVE_DBG"); dbg = e ? atoi(e) : 0; }

@@ -94,6 +94,8 @@ void build_solve_plan_host(const eigd_symbolic* S, int target_warps, int nslots,
 
   // ---- tiles and phases ---------------------------------------------------------------------
   P.tiles.clear();
+  P.deps.clear();
+  P.dep_ovf.clear();
   P.phases.clear();
   auto rec = [&](int k, int tile) {
     TileRec r;
@@ -153,7 +155,10 @@ void build_solve_plan_host(const eigd_symbolic* S, int target_warps, int nslots,
         P.sub_ptr.push_back((int)P.tiles.size());
         for (int k : bucket[(size_t)s * nl + l]) {
           int outs = dir == 0 ? sn_fsize(S, k) : sn_ncols(S, k);
-          for (int t = 0; t * SOLVE_TILE < outs && (t == 0 || !front_mode); ++t) P.tiles.push_back(rec(k, t));
+          for (int t = 0; t * SOLVE_TILE < outs && (t == 0 || !front_mode); ++t) {
+            P.tiles.push_back(rec(k, t));
+            P.deps.push_back(TileDep{0, 0, 0, 0, 0, 0, 0, 0});
+          }
         }
       }
       P.sub_ptr.push_back((int)P.tiles.size());
@@ -175,10 +180,30 @@ void build_solve_plan_host(const eigd_symbolic* S, int target_warps, int nslots,
     }
     const int ws = pick_ws((int)nt, redmax, target_warps);
     PhaseRec ph{dir, ws, 0, l, (int64_t)P.tiles.size(), to};
+    auto ntile = [&](int k, int d) { return ((d == 0 ? sn_fsize(S, k) : sn_ncols(S, k)) + to - 1) / to; };
     for (int q = S->level_ptr[l]; q < S->level_ptr[l + 1]; ++q) {
       int k = S->level_sn[q];
       int outs = dir == 0 ? sn_fsize(S, k) : sn_ncols(S, k);
-      for (int t = 0; t * to < outs; ++t) P.tiles.push_back(rec(k, t));
+      // completion-counter dependencies of the front's tiles (see TileDep)
+      std::vector<std::pair<int, int>> dl;
+      if (dir == 0) {
+        for (int c = S->child_ptr[k]; c < S->child_ptr[k + 1]; ++c) {
+          int ch = S->child_idx[c];
+          if (S->sn_level[ch] > cut) dl.emplace_back(2 * ch, ntile(ch, 0));
+        }
+      } else {
+        int p = S->sn_parent[k];
+        if (p >= 0) dl.emplace_back(2 * p + 1, ntile(p, 1));
+        else dl.emplace_back(2 * k, ntile(k, 0));
+      }
+      TileDep td{2 * k + dir, (int)dl.size(), 0, 0, 0, 0, 0, 0};
+      if (dl.size() > 0) { td.d0 = dl[0].first; td.n0 = dl[0].second; }
+      if (dl.size() > 1) { td.d1 = dl[1].first; td.n1 = dl[1].second; }
+      if (dl.size() > 2) {
+        td.ovf = (int)P.dep_ovf.size();
+        for (size_t i = 2; i < dl.size(); ++i) { P.dep_ovf.push_back(dl[i].first); P.dep_ovf.push_back(dl[i].second); }
+      }
+      for (int t = 0; t * to < outs; ++t) { P.tiles.push_back(rec(k, t)); P.deps.push_back(td); }
     }
     ph.ntiles = (int)((int64_t)P.tiles.size() - ph.tile_off);
     P.phases.push_back(ph);
@@ -225,6 +250,16 @@ extern "C" int64_t eigd_solve_plan_get(const eigd_symbolic* s, int target_warps,
     case 5: return copy_out64(P.sub_ptr, out, cap);
     case 6: return copy_out64(P.sub_slot, out, cap);
     case 8: return copy_out64(P.slab, out, cap);
+    case 9: {
+      std::vector<int64_t> flat;
+      flat.reserve(P.deps.size() * 8);
+      for (const TileDep& d : P.deps) {
+        int64_t a[8] = {d.self, d.ndep, d.d0, d.n0, d.d1, d.n1, d.ovf, d.pad};
+        flat.insert(flat.end(), a, a + 8);
+      }
+      return copy_out64(flat, out, cap);
+    }
+    case 10: return copy_out64(P.dep_ovf, out, cap);
     case 7: {
       std::vector<int64_t> v{P.cut_level, P.nslots, P.nfwd};
       return copy_out64(v, out, cap);

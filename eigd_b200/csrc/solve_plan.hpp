@@ -44,8 +44,28 @@ struct TileRec {
 };
 static_assert(sizeof(TileRec) == 48, "TileRec is read as three 16-byte words");
 
-// One phase = the tiles of one level of the assembly tree in one direction; phases are separated
-// by a grid-wide barrier.  ws warps share a tile (they split its reduction dimension).
+// Dependencies of one LEVEL-phase tile (same index as its TileRec).  The level phases are not separated by grid
+// barriers: every front above the cut owns two completion counters (forward: 2 * sn, backward: 2 * sn + 1) that
+// each finished tile of the front increments once per solve; a tile starts when the counters of the fronts it
+// reads from have reached (solve epoch) x (their tile count):
+//   forward  tile of front P : the forward counters of P's children above the cut (children below the cut were
+//                              finished by the subtree launch that precedes the level kernel in stream order);
+//   backward tile of front F : the backward counter of F's parent (which transitively covers every ancestor and
+//                              the whole forward sweep); a root waits for its own forward counter.
+// Two dependencies travel inline, further ones (fronts with three or more children above the cut) in dep_ovf as
+// (counter, tile count) pairs starting at `ovf`.
+struct TileDep {
+  int self;       // counter this tile increments when its outputs are stored
+  int ndep;       // number of dependencies
+  int d0, n0;     // counter index / tiles per solve of dependency 0
+  int d1, n1;     // ... of dependency 1
+  int ovf;        // offset of dependencies 2 .. ndep-1 in SolvePlanHost::dep_ovf (pairs)
+  int pad;
+};
+static_assert(sizeof(TileDep) == 32, "TileDep is read as two 16-byte words");
+
+// One phase = the tiles of one level of the assembly tree in one direction.  Level phases are ordered (every CTA
+// walks them in sequence) but synchronised tile by tile through TileDep, not by a grid-wide barrier.  ws warps share a tile (they split its reduction dimension).
 // ws == 0 marks a SUBTREE phase: the bottom levels 0..cut of the tree are partitioned into complete
 // subtrees, every subtree is owned by one CTA slot, and the slot walks its levels with CTA-local
 // barriers only (no grid barrier below the cut).  For such a phase ntiles = cut + 1 (local levels),
@@ -66,6 +86,8 @@ struct SolvePlanHost {
   std::vector<int> ovf;
   std::vector<int> slab;          // per supernode: 0, 1, 2 or 255 (root)
   std::vector<TileRec> tiles;
+  std::vector<TileDep> deps;      // parallel to tiles (all-zero for the tiles of the subtree phases)
+  std::vector<int> dep_ovf;       // (counter, tile count) pairs of the third and later dependencies
   std::vector<PhaseRec> phases;   // forward phases (leaves -> root) then backward phases (root -> leaves)
   int nfwd = 0;
   int cut_level = -1;             // levels <= cut_level are executed by the subtree phases (-1: none)

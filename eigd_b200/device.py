@@ -640,6 +640,37 @@ def lanczos_extend(op, Bip, Vt, BVt, j0, j1, w, h, g, ab):
         Timeline.end(tok, 0, launch_count() - l0)
 
 
+def block_lanczos_start(Bip, Vt, BVt, P, scratch):
+    """B-orthonormalise the P start vectors Vt[:P] in place, BVt[:P] = B Vt[:P] (csrc/block_krylov.cu)."""
+    n = Vt.shape[1]
+    check(_lib.load().eigd_block_lanczos_start(n, int(P), _ptr(Bip.indptr), _ptr(Bip.indices), _ptr(Bip.data), _ptr(Vt), _ptr(BVt),
+                                               Vt.stride(0), _ptr(scratch), _ptr(_State.work)), "block_lanczos_start")
+
+
+def block_lanczos_extend(op, Bip, Vt, BVt, P, j0, m0, ncv, Ablk, Rblk, H1, H2, scratch):
+    """Block steps j0, j0 + P, ... < ncv of the shift-and-invert block Lanczos recurrence on the device.
+
+    op: SpLuOperator; Bip: CsrDevice of the inner product; Vt, BVt: (ncv + P, n) row-major bases holding m0 vectors;
+    Ablk, Rblk: (nsteps, P, P) device outputs (diagonal / sub-diagonal blocks of the projected operator)."""
+    n = Vt.shape[1]
+    for t in (Vt, BVt, Ablk, Rblk, H1, H2, scratch):
+        _chk(t)
+    if not (Vt.is_contiguous() and BVt.is_contiguous()):
+        raise ValueError("block_lanczos_extend needs contiguous row-major bases")
+    refine = int(getattr(op, "refine", 0))
+    work2 = empty(2 * P * n) if refine else None
+    mat = op.mat
+    tok = Timeline.begin("lanczos")
+    l0 = launch_count() if tok else 0
+    check(_lib.load().eigd_block_lanczos_extend(op.lu.handle, refine, n, int(P), _ptr(mat.indptr), _ptr(mat.indices), _ptr(mat.data),
+                                                _ptr(Bip.indptr), _ptr(Bip.indices), _ptr(Bip.data), _ptr(Vt), _ptr(BVt),
+                                                Vt.stride(0), int(j0), int(m0), int(ncv), _ptr(Ablk), _ptr(Rblk), _ptr(H1), _ptr(H2),
+                                                _ptr(scratch), _ptr(_State.work), _ptr(work2)), "block_lanczos_extend")
+    op.count += int(ncv) - int(j0)          # one operator application per new basis vector, as SpLuOperator counts columns
+    if tok:
+        Timeline.end(tok, 0, launch_count() - l0)
+
+
 # ------------------------------------------------------------------------------------------
 # element kernels
 # ------------------------------------------------------------------------------------------

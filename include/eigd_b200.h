@@ -132,6 +132,9 @@ int eigd_solve_timing_end(int64_t* calls_by_k, double* ms_by_k);
 /* developer profiling of the persistent solve kernel: d_buf (device, (nphases + 1) x uint64) receives the
  * %globaltimer of CTA 0 at kernel start and after every phase of the following solves; NULL switches it off */
 int eigd_solve_set_phase_times(void* d_buf);
+/* developer profiling: d_buf (device, 8 x nphases int64) receives clock64 stamps of CTA 0 / warp 0 inside its first
+ * tile of every level phase (start, dependencies met, product done, partials reduced, stored, signalled) */
+int eigd_solve_set_trace(void* d_buf);
 int eigd_solve_num_phases(const eigd_factor* f);
 int64_t eigd_factor_bytes(const eigd_factor* f);
 
@@ -149,6 +152,21 @@ int eigd_lanczos_extend(eigd_factor* f, int refine, int n, const int* d_mat_indp
                         const double* d_b_vals, double* d_V, double* d_BV, int64_t ld, int j0, int j1,
                         double* d_w, double* d_h, double* d_g, double* d_ab, int ldab, double* d_work,
                         double* d_work2);
+
+/* ---- BLOCK version of the recurrence (block size P = 2 .. 4; csrc/block_krylov.cu): one call runs the block steps
+ *      j = j0, j0 + P, ... < ncv of a restart cycle on the device.  V, BV: (ncv + P) x n row-major (leading dimension
+ *      ld) holding m0 >= j0 + P B-orthonormal vectors on entry and ncv + P on exit.  Per step s the P x P diagonal
+ *      block (H1 + H2)[j : j + P] goes to Ablk[s] and the sub-diagonal block R (W = V_new R) to Rblk[s] (row-major);
+ *      a rank-deficient block (breakdown) is flagged by NaNs in Rblk.  H1, H2: (ncv + P) * P doubles; scratch: 3 P^2;
+ *      work >= eigd_gemm_tn_workspace(); work2: 2 P n doubles (refinement only). ------------------------------ */
+int eigd_block_lanczos_extend(eigd_factor* f, int refine, int n, int P, const int* d_mat_indptr, const int* d_mat_indices,
+                              const double* d_mat_vals, const int* d_b_indptr, const int* d_b_indices,
+                              const double* d_b_vals, double* d_V, double* d_BV, int64_t ld, int j0, int m0, int ncv,
+                              double* d_Ablk, double* d_Rblk, double* d_H1, double* d_H2, double* d_scratch,
+                              double* d_work, double* d_work2);
+/* B-orthonormalise the P start vectors V[0:P] (rows) in place and set BV[0:P] = B V[0:P]; scratch: 3 P^2 doubles */
+int eigd_block_lanczos_start(int n, int P, const int* d_b_indptr, const int* d_b_indices, const double* d_b_vals,
+                             double* d_V, double* d_BV, int64_t ld, double* d_scratch, double* d_work);
 
 /* ---- element kernels: replaces the numpy einsum callbacks and assembly in
  *      examples/thermal.py:126-246, examples/natural_frequency.py:134-284 ------------------ */

@@ -28,10 +28,22 @@ def plan_arrays(sym, target_warps, nslots, cut):
         return out[:cnt]
 
     return {"ovf_row": get(1), "ovf": get(2), "tiles": get(3).reshape(-1, 8), "phases": get(4).reshape(-1, 6),
-            "sub_ptr": get(5), "sub_slot": get(6), "meta": get(7), "slab": get(8)}
+            "sub_ptr": get(5), "sub_slot": get(6), "meta": get(7), "slab": get(8), "deps": get(9).reshape(-1, 8),
+            "dep_ovf": get(10)}
 
 
-def emulate(plan, S, sym_arr, dinv, b):
+def tile_deps(plan, te):
+    """[(counter, tiles per solve), ...] of tile te (TileDep, solve_plan.hpp)."""
+    selfc, ndep, d0, n0, d1, n1, ovf, _ = (int(v) for v in plan["deps"][te])
+    out = [(d0, n0), (d1, n1)][:min(ndep, 2)]
+    for q in range(2, ndep):
+        out.append((int(plan["dep_ovf"][ovf + 2 * (q - 2)]), int(plan["dep_ovf"][ovf + 2 * (q - 2) + 1])))
+    return selfc, out
+
+
+def emulate(plan, S, sym_arr, dinv, b, shuffle=None):
+    """shuffle: a numpy Generator -> the level-phase tiles run in a RANDOM order constrained only by their
+    completion-counter dependencies (what the barrier-free kernel guarantees), instead of the plan order."""
     perm, sn_rows, rel = sym_arr["perm"], sym_arr["sn_rows"], sym_arr["rel"]
     n = len(perm)
     sumf = len(plan["ovf_row"])
@@ -82,7 +94,28 @@ def emulate(plan, S, sym_arr, dinv, b):
                 xp[first + out] = Sk[o0:, out] @ vec[o0:]
 
     tiles = plan["tiles"]
+    cnt = {}
+    pending = []                       # level-phase tiles not yet run: (te, direction)
+
+    def run_level_tile(te, d):
+        selfc, deps = tile_deps(plan, te)
+        assert all(cnt.get(c, 0) >= need for c, need in deps), "dependency not complete in plan order"
+        do_tile(d, tiles[te])
+        cnt[selfc] = cnt.get(selfc, 0) + 1
+
+    def drain():
+        # random topological execution: any tile whose counters are complete may run next
+        while pending:
+            ready = [i for i, (te, d) in enumerate(pending)
+                     if all(cnt.get(c, 0) >= need for c, need in tile_deps(plan, te)[1])]
+            assert ready, "deadlock: no runnable tile"
+            i = ready[int(shuffle.integers(len(ready)))]
+            te, d = pending.pop(i)
+            run_level_tile(te, d)
+
     for d, ws, ntiles, level, tile_off, _to in plan["phases"]:
+        if ws == 0 and pending:
+            drain()                    # the kernel puts a grid barrier in front of an in-kernel subtree phase
         if ws == 0:
             nl, nslots = int(ntiles), int(level)
             for slot in range(nslots):
@@ -102,7 +135,12 @@ def emulate(plan, S, sym_arr, dinv, b):
                             do_tile(int(d), tiles[te])
         else:
             for te in range(tile_off, tile_off + ntiles):
-                do_tile(int(d), tiles[te])
+                if shuffle is None:
+                    run_level_tile(te, int(d))
+                else:
+                    pending.append((te, int(d)))
+    if pending:
+        drain()
     x = np.empty(n)
     x[perm] = xp
     return x, done
@@ -145,6 +183,9 @@ def test_plan_emulation_matches_scipy(nx, ny, dof, use_coords):
         plan = plan_arrays(sym, target_warps, nslots, cut)
         x, done = emulate(plan, S, arr, orc.dinv, b)
         assert np.abs(x - x_ref).max() <= 1e-10 * np.abs(x_ref).max(), (target_warps, nslots, cut)
+        # the completion counters alone order the level phases correctly: random dependency-respecting schedules
+        xs, _ = emulate(plan, S, arr, orc.dinv, b, shuffle=np.random.default_rng(target_warps + nslots))
+        assert np.array_equal(xs, x), (target_warps, nslots, cut)
         # every tile of every front is scheduled exactly once per direction
         assert len([1 for k in done if k[0] == 0]) == ntiles_f
         assert len([1 for k in done if k[0] == 1]) == ntiles_b
