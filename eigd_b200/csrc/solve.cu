@@ -187,10 +187,15 @@ __device__ __forceinline__ void signal_done(unsigned* c) {
   if ((threadIdx.x & 31) == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(c) : "memory");
 }
 
-template <int KT, int MC, class StageFn, class WaitFn>
+// TH = tile height (outputs per warp tile): 32 (lane = output), or 16 / 8 on the upper levels, where a level has too few
+// 32-output tiles to occupy the SMs and a 32-row slice of a wide front would make ONE SM stream 64 - 128 KB (its
+// load path, ~64 B per clock, is then the bound).  With TH < 32 the lanes form 32 / TH groups that share the
+// columns of a chunk (group g takes columns g, g + 32 / TH, ...) and meet in a shuffle reduction at the end.
+template <int KT, int MC, int TH, class StageFn, class WaitFn>
 __device__ __forceinline__ void warp_panel_product(const double* __restrict__ M, int64_t ld, int c0, int c1, int lane,
                                                    double* stage, double* acc, StageFn stage_fn, WaitFn& wait) {
-  constexpr int g = 0, nks = 1;
+  constexpr int nks = 32 / TH;
+  const int g = lane / TH;
   for (int cc = c0; cc < c1; cc += 32) {
     const int ncol = min(32, c1 - cc);
     const double* Mc = M + (int64_t)(cc + g) * ld;
@@ -210,7 +215,7 @@ __device__ __forceinline__ void warp_panel_product(const double* __restrict__ M,
     for (int j = 0; j < MC; ++j)
 #pragma unroll
       for (int r = 0; r < KT; ++r) acc[r] = fma(m[j], stage[r * 32 + ((g + j * nks) & 31)], acc[r]);
-    if (MC < 32) {
+    if (MC * nks < 32) {
       for (int j0 = MC; g + j0 * nks < ncol; j0 += MC) {          // warp-uniform trip count is not needed: no sync inside
 #pragma unroll
         for (int j = 0; j < MC; ++j) m[j] = (g + (j0 + j) * nks < ncol) ? __ldg(Mc + (j0 + j) * step) : 0.0;
@@ -244,10 +249,11 @@ __host__ __device__ inline bool barrier_between(const PhaseRec& a, const PhaseRe
 // the products of one warp tile: slice `slice` of `ws` of the reduction dimension.
 // use_perm: the right-hand side is gathered from B through perm (first phase; later phases read the
 // permuted copy written during the first one)
-template <int KT, int MC = DefaultMC<KT>::value, class WaitFn>
+template <int KT, int MC = DefaultMC<KT>::value, int TH = SOLVE_TILE, class WaitFn>
 __device__ __forceinline__ void tile_compute(const SolveArgs& a, int dir, bool use_perm, const TileRec& tr, int lane,
                                              int slice, int ws, double* stage, double* acc, WaitFn& wait) {
-  constexpr int to = SOLVE_TILE;
+  constexpr int to = TH;
+  constexpr int MCT = MC < TH ? MC : TH;               // loads in flight per lane and chunk: a chunk has TH columns per lane group
   const int k = a.k;
   const int nc = tr.nc, f = tr.nc + tr.nb;
   const int o0 = tr.tile * to;
@@ -258,7 +264,7 @@ __device__ __forceinline__ void tile_compute(const SolveArgs& a, int dir, bool u
     const int per = (cend + ws - 1) / ws;
     const int c0 = slice * per, c1 = min(cend, c0 + per);
     const double* M = a.sfwd + tr.soff + min(out, f - 1);
-    warp_panel_product<KT, MC>(M, f, c0, c1, lane, stage, acc, [&](int c, double* v) {
+    warp_panel_product<KT, MCT, TH>(M, f, c0, c1, lane, stage, acc, [&](int c, double* v) {
       if (use_perm) {
         const int64_t po = __ldg(&a.perm[tr.first + c]);
         const double* bp = a.B + po * a.brs;
@@ -271,6 +277,12 @@ __device__ __forceinline__ void tile_compute(const SolveArgs& a, int dir, bool u
       child_add<KT>(a, tr.w_off + c, tr.link, v);
     }, wait);
     wait(lane);
+    if (TH < 32) {
+#pragma unroll
+      for (int o = TH; o < 32; o <<= 1)
+#pragma unroll
+        for (int r = 0; r < KT; ++r) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
+    }
     if (slice == 0 && lane < to && out >= nc && out < f) {
       double cu[KT];                                    // the children's updates of this output row
 #pragma unroll
@@ -285,19 +297,26 @@ __device__ __forceinline__ void tile_compute(const SolveArgs& a, int dir, bool u
     const int per = (len + ws - 1) / ws;
     const int i0 = o0 + slice * per, i1 = min(f, i0 + per);
     const double* M = a.sbwd + tr.soff + min(out, nc - 1);
-    warp_panel_product<KT, MC>(M, nc, i0, i1, lane, stage, acc, [&](int i, double* v) {
+    warp_panel_product<KT, MCT, TH>(M, nc, i0, i1, lane, stage, acc, [&](int i, double* v) {
       if (i < nc) add_row<KT>(a.ybuf, tr.first + i, k, v);
       else add_row<KT>(a.xperm, __ldg(&a.sn_rows[tr.row_off + i - nc]), k, v);
     }, wait);
     wait(lane);
+    if (TH < 32) {
+#pragma unroll
+      for (int o = TH; o < 32; o <<= 1)
+#pragma unroll
+        for (int r = 0; r < KT; ++r) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
+    }
   }
 }
 
-template <int KT>
+template <int KT, int TH = SOLVE_TILE>
 __device__ __forceinline__ void tile_store(const SolveArgs& a, int dir, const TileRec& tr, int lane, const double* acc) {
   const int k = a.k;
   const int nc = tr.nc, f = tr.nc + tr.nb;
-  const int out = tr.tile * SOLVE_TILE + lane;
+  const int out = tr.tile * TH + lane;
+  if (TH < 32 && lane >= TH) return;
   if (dir == 0) {
     if (out < nc) {
       const double di = __ldg(&a.dinv[tr.first + out]);
@@ -748,6 +767,77 @@ __global__ void __launch_bounds__(NW * 32, 1) subtree_kernel(SolveArgs a, int p)
   }
 }
 
+// One level phase: the tiles (height TH) of one level of the tree in one direction, CTA-strided; ws warps share a tile
+// and split its reduction dimension.  A tile waits for the completion counters of the fronts it reads from and
+// increments its own front's counter when its outputs are stored (no grid barrier).
+template <int KT, int TH>
+__device__ __forceinline__ void level_phase(const SolveArgs& a, const PhaseRec& ph, int p, bool use_perm, int lane, int warp,
+                                            double* stage, double* part, bool have_next, int4 (*s_next)[5]) {
+  const int64_t tile_off = ph.tile_off;
+  const int dir = ph.dir, ws = ph.ws, ntiles = ph.ntiles;
+  const int tpc = SOLVE_WARPS / ws;
+  const int sub = warp / ws, slice = warp - sub * ws;
+  const int nct = (ntiles + tpc - 1) / tpc;
+  for (int ct = blockIdx.x; ct < nct; ct += gridDim.x) {
+    const int te = ct * tpc + sub;
+    const bool have = te < ntiles;
+    double acc[KT];
+#pragma unroll
+    for (int r = 0; r < KT; ++r) acc[r] = 0.0;
+    TileRec tr;
+    tr.first = tr.nc = tr.nb = tr.tile = 0;
+    tr.soff = tr.w_off = tr.row_off = tr.link = 0;
+    DepWait dw;
+    dw.cnt = a.cnt;
+    dw.ovf = a.dep_ovf;
+    dw.epoch = a.epoch;
+    dw.pending = false;
+    dw.td.self = 0;
+    if (have) {
+      int4 d0, d1;
+      if (have_next && ct == (int)blockIdx.x) {
+        tr = unpack_tile(s_next[warp][0], s_next[warp][1], s_next[warp][2]);
+        d0 = s_next[warp][3];
+        d1 = s_next[warp][4];
+      } else {
+        tr = load_tile(a.tiles + tile_off + te);
+        const int4* q = reinterpret_cast<const int4*>(a.deps + tile_off + te);
+        d0 = __ldg(q);
+        d1 = __ldg(q + 1);
+      }
+      dw.td.self = d0.x; dw.td.ndep = d0.y; dw.td.d0 = d0.z; dw.td.n0 = d0.w;
+      dw.td.d1 = d1.x; dw.td.n1 = d1.y; dw.td.ovf = d1.z; dw.td.pad = 0;
+      dw.pending = dw.td.ndep > 0;
+      const bool tr_on = a.trace && blockIdx.x == 0 && ct == 0 && threadIdx.x == 0;
+      if (tr_on) a.trace[8 * p + 0] = clock64();
+      if (a.trace) {              // trace build of the chain: wait first so that the segments separate
+        dw(lane);
+        if (tr_on) a.trace[8 * p + 1] = clock64();
+      }
+      tile_compute<KT, DefaultMC<KT>::value, TH>(a, dir, use_perm, tr, lane, slice, ws, stage, acc, dw);
+      if (tr_on) a.trace[8 * p + 2] = clock64();
+    }
+    if (ws > 1) {
+#pragma unroll
+      for (int r = 0; r < KT; ++r) part[(warp * KT + r) * 32 + lane] = acc[r];
+      __syncthreads();
+      if (have && slice == 0)
+        for (int s = 1; s < ws; ++s)
+#pragma unroll
+          for (int r = 0; r < KT; ++r) acc[r] += part[((warp + s) * KT + r) * 32 + lane];
+    }
+    const bool tr_on2 = a.trace && blockIdx.x == 0 && ct == 0 && threadIdx.x == 0;
+    if (tr_on2) a.trace[8 * p + 3] = clock64();
+    if (have && slice == 0) {
+      tile_store<KT, TH>(a, dir, tr, lane, acc);
+      if (tr_on2) a.trace[8 * p + 4] = clock64();
+      signal_done(a.cnt + dw.td.self);
+      if (tr_on2) a.trace[8 * p + 5] = clock64();
+    }
+    if (ws > 1) __syncthreads();
+  }
+}
+
 // The phases [a.p_begin, a.p_end) as one persistent cooperative kernel.  Level phases follow each other WITHOUT a
 // grid barrier: tiles are handed out in a fixed global order (phase by phase, CTA-strided inside a phase), every CTA
 // walks its share in that order, and a tile spins only on the completion counters of the fronts it reads from
@@ -824,68 +914,12 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32, 1) solve_kernel(SolveArgs a)
           __syncthreads();      // CTA-scope ordering: the level's results are visible to the whole slot
         }
       }
+    } else if (ph.pad == 8) {
+      level_phase<KT, 8>(a, ph, p, use_perm, lane, warp, stage, part, have_next, s_next);
+    } else if (ph.pad == 16) {
+      level_phase<KT, 16>(a, ph, p, use_perm, lane, warp, stage, part, have_next, s_next);
     } else {
-      const int tpc = SOLVE_WARPS / ws;
-      const int sub = warp / ws, slice = warp - sub * ws;
-      const int nct = (ntiles + tpc - 1) / tpc;
-      for (int ct = blockIdx.x; ct < nct; ct += gridDim.x) {
-        const int te = ct * tpc + sub;
-        const bool have = te < ntiles;
-        double acc[KT];
-#pragma unroll
-        for (int r = 0; r < KT; ++r) acc[r] = 0.0;
-        TileRec tr;
-        tr.first = tr.nc = tr.nb = tr.tile = 0;
-        tr.soff = tr.w_off = tr.row_off = tr.link = 0;
-        DepWait dw;
-        dw.cnt = a.cnt;
-        dw.ovf = a.dep_ovf;
-        dw.epoch = a.epoch;
-        dw.pending = false;
-        dw.td.self = 0;
-        if (have) {
-          int4 d0, d1;
-          if (have_next && ct == (int)blockIdx.x) {
-            tr = unpack_tile(s_next[warp][0], s_next[warp][1], s_next[warp][2]);
-            d0 = s_next[warp][3];
-            d1 = s_next[warp][4];
-          } else {
-            tr = load_tile(a.tiles + tile_off + te);
-            const int4* q = reinterpret_cast<const int4*>(a.deps + tile_off + te);
-            d0 = __ldg(q);
-            d1 = __ldg(q + 1);
-          }
-          dw.td.self = d0.x; dw.td.ndep = d0.y; dw.td.d0 = d0.z; dw.td.n0 = d0.w;
-          dw.td.d1 = d1.x; dw.td.n1 = d1.y; dw.td.ovf = d1.z; dw.td.pad = 0;
-          dw.pending = dw.td.ndep > 0;
-          const bool tr_on = a.trace && blockIdx.x == 0 && ct == 0 && threadIdx.x == 0;
-          if (tr_on) a.trace[8 * p + 0] = clock64();
-          if (a.trace) {              // trace build of the chain: wait first so that the segments separate
-            dw(lane);
-            if (tr_on) a.trace[8 * p + 1] = clock64();
-          }
-          tile_compute<KT>(a, dir, use_perm, tr, lane, slice, ws, stage, acc, dw);
-          if (tr_on) a.trace[8 * p + 2] = clock64();
-        }
-        if (ws > 1) {
-#pragma unroll
-          for (int r = 0; r < KT; ++r) part[(warp * KT + r) * 32 + lane] = acc[r];
-          __syncthreads();
-          if (have && slice == 0)
-            for (int s = 1; s < ws; ++s)
-#pragma unroll
-              for (int r = 0; r < KT; ++r) acc[r] += part[((warp + s) * KT + r) * 32 + lane];
-        }
-        const bool tr_on2 = a.trace && blockIdx.x == 0 && ct == 0 && threadIdx.x == 0;
-        if (tr_on2) a.trace[8 * p + 3] = clock64();
-        if (have && slice == 0) {
-          tile_store<KT>(a, dir, tr, lane, acc);
-          if (tr_on2) a.trace[8 * p + 4] = clock64();
-          signal_done(a.cnt + dw.td.self);
-          if (tr_on2) a.trace[8 * p + 5] = clock64();
-        }
-        if (ws > 1) __syncthreads();
-      }
+      level_phase<KT, SOLVE_TILE>(a, ph, p, use_perm, lane, warp, stage, part, have_next, s_next);
     }
     // ---- hand the prefetched first tile record of the next phase to the whole warp
     have_next = nxt_have;

@@ -14,7 +14,7 @@ int pick_ws(int ntiles, int redmax, int target_warps) {
   // split the reduction dimension of a tile over ws warps while (i) the level would otherwise leave
   // most resident warps idle and (ii) every warp still gets >= 8 terms
   int ws = 1;
-  while (ws < SOLVE_WARPS && (int64_t)ntiles * ws * 2 <= target_warps && redmax / (2 * ws) >= 8) ws *= 2;
+  while (ws < SOLVE_WARPS && (int64_t)ntiles * ws * 2 <= target_warps && redmax / (2 * ws) >= 4) ws *= 2;
   return ws;
 }
 
@@ -166,21 +166,44 @@ void build_solve_plan_host(const eigd_symbolic* S, int target_warps, int nslots,
     P.phases.push_back(ph);
   };
   if (cut >= 0) subtree_phase(0);
-  // level phase.  (A variable tile height -- 16 / 8 / 4 outputs per warp tile with the lane groups splitting
-  // the reduction, to spread the few large fronts near the root over more SMs -- was measured SLOWER on
-  // B200, 380 us against 290 us per single-RHS solve at 251k DOF, and was removed; see DESIGN.md.)
+  // Tile height of a level phase: 32 outputs per warp tile, or 16 / 8 where a level has so few 32-output tiles that most
+  // SMs would idle while a few of them stream 64 - 128 KB panel slices each (the upper levels: one to a few dozen wide
+  // fronts).  With per-front completion counters instead of grid barriers a finer tiling costs no extra synchronisation.
+  // (Round 1 measured a variable tile height as slower -- with a grid barrier per level and the tile-serial overheads of
+  // that kernel; EIGD_SOLVE_THIN=0 restores 32 everywhere for comparison runs.)
+  bool thin = true;
+  if (const char* e = getenv("EIGD_SOLVE_THIN")) thin = atoi(e) != 0;
+  auto count_tiles = [&](int dir, int l, int to) {
+    int64_t nt = 0;
+    for (int q = S->level_ptr[l]; q < S->level_ptr[l + 1]; ++q) {
+      int k = S->level_sn[q];
+      nt += ((dir == 0 ? sn_fsize(S, k) : sn_ncols(S, k)) + to - 1) / to;
+    }
+    return nt;
+  };
+  const int ncta = std::max(1, target_warps / SOLVE_WARPS);
+  std::vector<int> height(2 * (size_t)S->nlevels, SOLVE_TILE);      // [dir * nlevels + level]
+  for (int dir = 0; dir < 2 && thin; ++dir)
+    for (int l = cut + 1; l < S->nlevels; ++l) {
+      int to = SOLVE_TILE;
+      while (to > 8 && count_tiles(dir, l, to / 2) <= ncta) to /= 2;
+      height[(size_t)dir * S->nlevels + l] = to;
+    }
   auto level_phase = [&](int dir, int l) {
     int redmax = 1;
-    int64_t nt = 0;
-    const int to = SOLVE_TILE;
+    const int to = height[(size_t)dir * S->nlevels + l];
     for (int q = S->level_ptr[l]; q < S->level_ptr[l + 1]; ++q) {
       int k = S->level_sn[q];
       redmax = std::max(redmax, dir == 0 ? sn_ncols(S, k) : sn_fsize(S, k));
-      nt += ((dir == 0 ? sn_fsize(S, k) : sn_ncols(S, k)) + to - 1) / to;
     }
+    const int64_t nt = count_tiles(dir, l, to);
     const int ws = pick_ws((int)nt, redmax, target_warps);
     PhaseRec ph{dir, ws, 0, l, (int64_t)P.tiles.size(), to};
-    auto ntile = [&](int k, int d) { return ((d == 0 ? sn_fsize(S, k) : sn_ncols(S, k)) + to - 1) / to; };
+    // tiles of front k in direction d, in the tile height of ITS level's phase (completion-counter targets)
+    auto ntile = [&](int k, int d) {
+      const int tk = S->sn_level[k] > cut ? height[(size_t)d * S->nlevels + S->sn_level[k]] : SOLVE_TILE;
+      return ((d == 0 ? sn_fsize(S, k) : sn_ncols(S, k)) + tk - 1) / tk;
+    };
     for (int q = S->level_ptr[l]; q < S->level_ptr[l + 1]; ++q) {
       int k = S->level_sn[q];
       int outs = dir == 0 ? sn_fsize(S, k) : sn_ncols(S, k);

@@ -1355,6 +1355,14 @@ class IRAM(_SolverBase):
         _check_mode(mode)
         self.mode = mode
         self.seed = None          # start-vector seed (scipy >= 1.15 draws it at random; None keeps that)
+        self.block_size = None    # Lanczos block size (None: arpack.BLOCK_SIZE; 1: single-vector recurrence)
+        # The reference pairs the returned eigenvectors with ``indices[:N]``, the N first Ritz values in its sorted order
+        # (:1960-1965).  When the shift lies inside the wanted spectrum (buckling, sigma above the first load factors)
+        # that is NOT the set the eigensolver returned (the N largest |theta|): the Lanczos-adjoint guess then carries
+        # components along Phi and the reference's gradient is wrong (BASELINE configs[2]: -11.90 against the finite-
+        # difference value -3.654, tests/test_fullsize_golden_gpu.py).  Default here: ``indices`` lists the returned
+        # pairs first (identical to the reference whenever the two sets coincide); True reproduces the reference.
+        self.reference_pairing = False
         self._Phi_d = None
 
     def solve(self, A, B, factor, sigma):
@@ -1369,7 +1377,7 @@ class IRAM(_SolverBase):
             # the adjoint columns gathered from the other ranks belong to different eigenvectors
             seed = 0
         lam, _, T, _, st = eigsh_mod(A0, M=self._Bd, OPinv=factor, k=self.N, sigma=sigma, which="LM", mode=self.mode,
-                                     tol=self.tol, ncv=self.m, return_state=True, seed=seed)
+                                     tol=self.tol, ncv=self.m, return_state=True, seed=seed, block=self.block_size)
         self.lam, self.T = lam, T
         self.lanczos_state = st
         self._V_d = st.Vt.T
@@ -1383,6 +1391,10 @@ class IRAM(_SolverBase):
         else:
             eigs = sigma * self.theta / (self.theta - 1.0)
             self.indices = np.argsort(-1.0 / eigs)
+        sel = set(int(i) for i in st.sel)
+        if not self.reference_pairing and set(int(i) for i in self.indices[: self.N]) != sel:
+            # the returned pairs first (in the sorted order), then the remaining Ritz pairs (see __init__)
+            self.indices = np.array([i for i in self.indices if int(i) in sel] + [i for i in self.indices if int(i) not in sel])
         if _is_close(eigs[self.indices[self.N - 1]], eigs[self.indices[self.N]], self.eig_atol):
             warnings.warn(f"IRAM: Ritz values {self.N} and {self.N+1} are numerically repeated.")   # :1967-1974
         # modal-assurance sign alignment of Y against the returned eigenvectors (:1978-1984):

@@ -322,6 +322,8 @@ class BucklingTopologyAnalysis:
                 self.m = max(2 * self.N + 1, 60)
             self.eig_solver = IRAM(N=self.N, m=self.m, eig_atol=self.eig_atol, mode="buckling")
             self.eig_solver.seed = self.seed
+            self.eig_solver.reference_pairing = getattr(self, "reference_pairing", False)
+            self.eig_solver.block_size = getattr(self, "block_size", None)
         else:
             if self.m is None:
                 self.m = max(3 * self.N + 1, 60)

@@ -95,23 +95,48 @@ def test_c5_natural_frequency_202k_design0_vs_reference():
     check_gradient(model.xb.cpu().numpy(), g)
 
 
-def test_c3_buckling_497k_vs_reference():
-    """buckling.make_model(nx=352, ny=704, N=20, m=60, sigma=3): indefinite K + sigma G (six buckling load factors
-    below the shift), x = 0.5, aggregate h = sum_i eta_i phi_i[node]^2 at the dof of largest |phi_1| (fixture)."""
+def _c3_gradient(g, reference_pairing=False, block_size=None):
     from eigd_b200 import device as D, topo as T
-    g = golden("c3")
     D.init()
     model = T.make_buckling_model(nx=int(g["nx"]), ny=int(g["ny"]), N=int(g["N"]), m=int(g["m"]), sigma=float(g["sigma"]),
                                   solver_type="IRAM", adjoint_method="sibk", adjoint_options={"lanczos_guess": True},
                                   rtol=1e-12, deriv_type="tensor")
+    model.reference_pairing, model.block_size = reference_pairing, block_size
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         model.initialize()
     model.initialize_adjoint()
     h = model.add_eigenvector_aggregate_derivative(1.0, 100.0, int(g["node"]), mode="tanh")
     model.finalize_adjoint()
-    assert rel(model.BLF, g["BLF"]) < 1e-10
-    assert abs(model.compliance() - float(g["compliance"])) <= 1e-9 * abs(float(g["compliance"]))
-    q = g["qnode"]                      # tanh weights saturate for these load factors: eta_i = 1 / N, h = mean_i phi_i[node]^2
+    return model, h
+
+
+def test_c3_buckling_497k_vs_reference():
+    """buckling.make_model(nx=352, ny=704, N=20, m=60, sigma=3): indefinite K + sigma G (six buckling load factors
+    below the shift), x = 0.5, aggregate h = sum_i eta_i phi_i[node]^2 at the dof of largest |phi_1| (fixture).
+
+    At this configuration the reference pairs the returned eigenvectors with the wrong Ritz pairs when it builds the
+    Lanczos-adjoint guess (IRAM.reference_pairing in eigd_b200/eigenvector_derivatives.py) and its gradient with
+    ``lanczos_guess=True`` disagrees with finite differences.  Pinned here:
+      * eigenvalues, compliance, eigenvector entries: against the reference (both fixtures);
+      * the gradient of the default path (guess ON, pairing fixed, block Lanczos): against the reference's own
+        gradient from a ZERO guess (fullsize_c3_noguess.npz), which is the finite-difference-consistent one;
+      * with reference_pairing=True and the single-vector recurrence: against the reference's guess-ON output
+        (fullsize_c3.npz) -- the reference reproduced including its defect."""
+    g0 = golden("c3_noguess")
+    model, h = _c3_gradient(g0)
+    assert rel(model.BLF, g0["BLF"]) < 1e-10
+    assert abs(model.compliance() - float(g0["compliance"])) <= 1e-9 * abs(float(g0["compliance"]))
+    q = g0["qnode"]                     # tanh weights saturate for these load factors: eta_i = 1 / N, h = mean_i phi_i[node]^2
     assert abs(h - float(np.mean(q * q))) <= 1e-8 * float(np.mean(q * q))
+    check_gradient(model.xb.cpu().numpy(), g0)
+    # finite-difference value of the directional derivative (tools/dbg_c3_fd.py, eps = 1e-5): -3.65414034
+    pert = np.random.default_rng(PERT_SEED).uniform(size=model.xb.shape[0])
+    assert abs(float(pert @ model.xb.cpu().numpy()) - (-3.65414034)) < 2e-6
+
+
+def test_c3_reference_pairing_reproduces_reference_output():
+    g = golden("c3")
+    model, _ = _c3_gradient(g, reference_pairing=True, block_size=1)
+    assert rel(model.BLF, g["BLF"]) < 1e-10
     check_gradient(model.xb.cpu().numpy(), g)

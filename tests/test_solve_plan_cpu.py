@@ -63,19 +63,19 @@ def emulate(plan, S, sym_arr, dinv, b, shuffle=None):
                 v += sum(wbuf[2, plan["ovf"][o + 1 + q]] for q in range(cnt))
         return v
 
-    def do_tile(direction, rec):
+    def do_tile(direction, rec, th=32):
         first, nc, nb, tile, soff, w_off, row_off, link = (int(v) for v in rec)
         f = nc + nb
-        o0 = tile * 32
+        o0 = tile * th
         Sk = S[first]
         assert Sk.shape == (f, nc)
         key = (direction, first, tile)
         assert key not in done, "tile scheduled twice"
         done.add(key)
         if direction == 0:
-            cend = min(nc, o0 + 32)
+            cend = min(nc, o0 + th)
             w1 = np.array([bperm[first + c] + child(w_off + c, link) for c in range(cend)])
-            for out in range(o0, min(o0 + 32, f)):
+            for out in range(o0, min(o0 + th, f)):
                 acc = Sk[out, :cend] @ w1
                 if out >= nc:
                     acc += child(w_off + out, link)
@@ -90,17 +90,24 @@ def emulate(plan, S, sym_arr, dinv, b, shuffle=None):
                         wbuf[2, w_off + out] = acc
         else:
             vec = np.concatenate([y[first:first + nc], xp[sn_rows[row_off:row_off + nb]]])
-            for out in range(o0, min(o0 + 32, nc)):
+            for out in range(o0, min(o0 + th, nc)):
                 xp[first + out] = Sk[o0:, out] @ vec[o0:]
 
     tiles = plan["tiles"]
     cnt = {}
     pending = []                       # level-phase tiles not yet run: (te, direction)
 
+    height = {}                        # tile index -> tile height of its level phase (PhaseRec.pad)
+    for d, ws, ntiles, level, tile_off, _to in plan["phases"]:
+        if ws > 0:
+            assert int(_to) in (8, 16, 32)
+            for te in range(tile_off, tile_off + ntiles):
+                height[int(te)] = int(_to)
+
     def run_level_tile(te, d):
         selfc, deps = tile_deps(plan, te)
         assert all(cnt.get(c, 0) >= need for c, need in deps), "dependency not complete in plan order"
-        do_tile(d, tiles[te])
+        do_tile(d, tiles[te], height[int(te)])
         cnt[selfc] = cnt.get(selfc, 0) + 1
 
     def drain():
@@ -186,9 +193,12 @@ def test_plan_emulation_matches_scipy(nx, ny, dof, use_coords):
         # the completion counters alone order the level phases correctly: random dependency-respecting schedules
         xs, _ = emulate(plan, S, arr, orc.dinv, b, shuffle=np.random.default_rng(target_warps + nslots))
         assert np.array_equal(xs, x), (target_warps, nslots, cut)
-        # every tile of every front is scheduled exactly once per direction
-        assert len([1 for k in done if k[0] == 0]) == ntiles_f
-        assert len([1 for k in done if k[0] == 1]) == ntiles_b
+        # every tile of every front is scheduled exactly once per direction (32-output tiles below the cut and wherever
+        # the level keeps the full height; thinner tiles only add to the count)
+        assert len([1 for k in done if k[0] == 0]) >= ntiles_f
+        assert len([1 for k in done if k[0] == 1]) >= ntiles_b
+        if int(plan["phases"][:, 5][plan["phases"][:, 1] > 0].min(initial=32)) == 32:
+            assert len([1 for k in done if k[0] == 0]) == ntiles_f and len([1 for k in done if k[0] == 1]) == ntiles_b
         cutl = int(plan["meta"][0])
         seen_cut.add(cutl)
         if cutl >= 0:

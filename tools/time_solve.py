@@ -45,7 +45,7 @@ from eigd_b200 import _lib
 lib = _lib.load()
 nph = lib.eigd_solve_num_phases(f.lu.handle)
 buf = torch.zeros(nph + 1, dtype=torch.int64, device="cuda")
-for k in ((1,) if os.environ.get("EIGD_SOLVE_DBG") else (1, 10)):
+for k in ((1,) if os.environ.get("EIGD_SOLVE_DBG") else (1, 2, 4, 10)):
     B = torch.randn(n, k, dtype=torch.float64, device="cuda")
     X = torch.empty_like(B)
     lib.eigd_solve_set_phase_times(ctypes.c_void_p(buf.data_ptr()))
