@@ -153,6 +153,21 @@ int eigd_lanczos_extend(eigd_factor* f, int refine, int n, const int* d_mat_indp
                         double* d_w, double* d_h, double* d_g, double* d_ab, int ldab, double* d_work,
                         double* d_work2);
 
+/* ---- operators on stored unit element matrices (csrc/stored_fe.cu): the CRM-like shell driver, replacing what TACS
+ *      does on the host in reference examples/crm.py:122-142 (assembleMatType) and :331-355 (addMatDVSensInnerProduct,
+ *      the per-mode "vector" derivative form).  Element matrices K_e = c1[e] E1_e + c3[e] E3_e, ne x ne row-major,
+ *      ne element dofs.  Assembly is gather-form through the (element, a, b) -> CSR source lists of
+ *      eigd_q4_assemble; a second matrix on the same pattern (F1, F3, d1, d3 -> vals2) is optional (NULL). ---- */
+int eigd_stored_assemble(int64_t nnz, const int64_t* d_src_ptr, const int64_t* d_src, int ne, const double* d_E1,
+                         const double* d_E3, const double* d_c1, const double* d_c3, double* d_vals, const double* d_F1,
+                         const double* d_F3, const double* d_d1, const double* d_d3, double* d_vals2);
+/* out[e] = sum_k W[dof(e,:), k]^T (c1[e] E1_e + c3[e] E3_e) V[dof(e,:), k]; dofmap (nelems x ne, -1 = constrained);
+ * W, V row-major (n, N) with leading dimension ld; ne in {8, 24} */
+int eigd_stored_quadform(int nelems, int ne, const int* d_dofmap, const double* d_E1, const double* d_E3, const double* d_c1,
+                         const double* d_c3, const double* d_W, const double* d_V, int N, int64_t ld, double* d_out);
+/* out[c] = scale * sum_{i in [seg_ptr[c], seg_ptr[c+1])} x[perm[i]] (perm NULL: identity): warp-shuffle segmented sum */
+int eigd_segment_sum(int nseg, const int* d_seg_ptr, const int* d_perm, const double* d_x, double scale, double* d_out);
+
 /* ---- BLOCK version of the recurrence (block size P = 2 .. 4; csrc/block_krylov.cu): one call runs the block steps
  *      j = j0, j0 + P, ... < ncv of a restart cycle on the device.  V, BV: (ncv + P) x n row-major (leading dimension
  *      ld) holding m0 >= j0 + P B-orthonormal vectors on entry and ncv + P on exit.  Per step s the P x P diagonal

@@ -177,6 +177,51 @@ def buckling_case(solver_type="BasicLanczos", methods=("sibk", "pcpg"), nx=16, n
     return out
 
 
+def shell_case(nx=16, ny=14, ncx=4, ncy=3, N=6, m=30, omega0=10.0, seed=5):
+    """The flow of examples/crm.py (:212-370) -- IRAM, sibk, modal compliance with f[1::6] = 1, add_eig_total_derivative in
+    its default per-mode "vector" form -- with the UNMODIFIED reference solvers on host matrices of the synthetic shell
+    (oracle/shell_oracle.py stands in for TACS)."""
+    sys.path.insert(0, os.path.join(HERE, "..", ".."))
+    import shell_oracle as so
+    from eigd_b200.shell import cylindrical_panel, shell_unit_matrices       # host-only numpy functions
+    ref = rl.load_reference()
+    conn, X, P = cylindrical_panel(nx, ny, 1.0, 0.9, 2.0)
+    E1, E3, F1, F3 = shell_unit_matrices(conn, X)
+    ei, ej = np.arange(nx * ny) % nx, np.arange(nx * ny) // nx
+    comp = (ei * ncx // nx) + ncx * (ej * ncy // ny)
+    nodes = np.arange((nx + 1) * (ny + 1)).reshape(nx + 1, ny + 1)
+    orc = so.ShellOracle(conn, X, comp, nodes[:, 0], E1, E3, F1, F3)
+    x = np.random.default_rng(seed).uniform(0.6, 1.4, orc.ncomp)
+    Kr, Mr = orc.assemble(x)
+    sigma = omega0 ** 2
+    factor = ref.SpLuOperator((Kr - sigma * Mr).tocsc())
+    es = ref.IRAM(N=N, m=m, eig_atol=1e-5)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        lam, Q = es.solve(Kr, Mr, factor, sigma)
+    f = np.zeros(orc.ndof_full)
+    f[1::6] = 1.0
+    fr = f[orc.reduced]
+    Qb, lamb = np.zeros(Q.shape), np.zeros(N)
+    comp_val = 0.0
+    for i in range(N):                                   # crm.py:267-293
+        val = Q[:, i].dot(fr)
+        comp_val += val * val / lam[i]
+        Qb[:, i] += 2.0 * val * fr / lam[i]
+        lamb[i] -= (val * val) / lam[i] ** 2
+    psi, corr = es.solve_adjoint(Qb, rtol=1e-12, method="sibk", **SIBK)
+    grad = np.zeros(orc.ncomp)
+    grad = ref.add_eig_total_derivative(lam, Q, lamb, Qb, psi, lambda w, v: orc.dK(x, w, v), lambda w, v: orc.dM(x, w, v), grad,
+                                        adj_corr_data=corr)
+    out = {}
+    out.update(csr_dict("A", Kr))
+    out.update(csr_dict("B", Mr))
+    out.update(dict(nx=nx, ny=ny, ncx=ncx, ncy=ncy, N=N, m=es.m, omega0=omega0, sigma=sigma, x=x, lam=lam.copy(), Phi=Q.copy(),
+                    Phib=Qb.copy(), lamb=lamb.copy(), psi=psi.copy(), grad=grad.copy(), compliance=comp_val,
+                    corr=corr_to_array(corr), comp=comp, conn=conn, X=X))
+    return out
+
+
 if __name__ == "__main__":
     if not rl.reference_available():
         raise SystemExit("reference tree not available; fixtures cannot be regenerated here")
@@ -185,6 +230,7 @@ if __name__ == "__main__":
         "thermal_iram": lambda: thermal_case("IRAM", ["sibk"]),
         "nf_iram": nf_case,
         "buckling_basiclanczos": buckling_case,
+        "shell_iram": shell_case,
     }
     only = set(sys.argv[1:])
     for name, fn in cases.items():
