@@ -99,8 +99,9 @@ def shell_unit_matrices(conn, X, E=73.1e9, nu=0.33, rho=2780.0, kshear=5.0 / 6.0
             Bs[:, 0, ity] = N[None, :]
             Bs[:, 1, iw] = Ny
             Bs[:, 1, itx] = -N[None, :]
-            K1 += np.einsum("e,eia,ij,ejb->eab", det, Bm, Dp, Bm) + kshear * G * np.einsum("e,eia,eib->eab", det, Bs, Bs)
-            K3 += np.einsum("e,eia,ij,ejb->eab", det, Bb, Dp / 12.0, Bb)
+            bt = lambda B: np.ascontiguousarray(B.transpose(0, 2, 1))   # noqa: E731
+            K1 += det[:, None, None] * (np.matmul(bt(Bm), np.matmul(Dp[None], Bm)) + kshear * G * np.matmul(bt(Bs), Bs))
+            K3 += det[:, None, None] * np.matmul(bt(Bb), np.matmul(Dp[None] / 12.0, Bb))
             NN = np.outer(N, N)
             for idx in (iu, iv, iw):
                 M1[:, idx[:, None], idx[None, :]] += rho * det[:, None, None] * NN[None]
@@ -110,7 +111,8 @@ def shell_unit_matrices(conn, X, E=73.1e9, nu=0.33, rho=2780.0, kshear=5.0 / 6.0
     T = np.zeros((ne, 24, 24))
     for a in range(8):
         T[:, 3 * a:3 * a + 3, 3 * a:3 * a + 3] = R
-    rot = lambda A: np.einsum("eia,eij,ejb->eab", T, A, T)          # noqa: E731   T^T A T
+    Tt = np.ascontiguousarray(T.transpose(0, 2, 1))
+    rot = lambda A: np.matmul(np.matmul(Tt, A), T)                  # noqa: E731   T^T A T (batched)
     return rot(K1), rot(K3), rot(M1), rot(M3)
 
 

@@ -28,13 +28,13 @@ def now():
 
 
 def residuals(model, A, B, lam, Phi_d, mode):
-    """max_i ||L_i phi_i|| / ||B phi_i|| and max |Phi^T B Phi - I| on the device."""
+    """max_i ||L_i phi_i|| / (||A phi_i|| + |lam_i| ||B phi_i||) and max |Phi^T B Phi - I| on the device."""
     from eigd_b200 import device as D
     import torch
     AP, BP = A.spmm(Phi_d), B.spmm(Phi_d)
     lam_d = torch.as_tensor(np.asarray(lam), device=Phi_d.device)
     R = (AP - BP * lam_d) if mode == "normal" else (BP + AP * lam_d)
-    res = (R.norm(dim=0) / BP.norm(dim=0)).max().item()
+    res = (R.norm(dim=0) / (AP.norm(dim=0) + (BP * lam_d).norm(dim=0))).max().item()      # relative to |A phi| + |lam B phi|
     G = D.gemm_tn(Phi_d, BP).cpu().numpy()
     return res, float(np.abs(G - np.eye(G.shape[0])).max())
 
