@@ -44,6 +44,7 @@ SIGNATURES = {
     "eigd_factor_destroy": (None, [c_ptr]),
     "eigd_factor_numeric": (c_int, [c_ptr, c_i64, c_ptr, c_ptr]),
     "eigd_factor_info": (c_int, [c_ptr, c_ptr]),
+    "eigd_dmma_peak": (c_int, [c_int, c_int, c_ptr]),
     "eigd_factor_solve": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_i64, c_i64, c_int]),
     "eigd_factor_bytes": (c_i64, [c_ptr]),
     "eigd_solve_timing_begin": (c_int, []),

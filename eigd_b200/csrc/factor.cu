@@ -21,6 +21,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 namespace {
@@ -741,8 +742,16 @@ extern "C" int eigd_factor_numeric(eigd_factor* f, int64_t nnz, const double* d_
   EIGD_CHECK_LAUNCH();
   EIGD_LAUNCH(scatter_values_kernel, g, 256, 0, nnz, d_vals, d_map, f->fronts);
   EIGD_CHECK_LAUNCH();
+  // developer profiling (EIGD_FACTOR_PROF=1): device time per launch kind, synchronising after every launch
+  static int prof = -1;
+  if (prof < 0) { const char* e = getenv("EIGD_FACTOR_PROF"); prof = e ? atoi(e) : 0; }
+  double kind_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int kind_n[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+  if (prof) { cudaEventCreate(&pe0); cudaEventCreate(&pe1); }
   for (const Launch& L : h->factor_plan) {
     const int2* t = h->tasks + L.off;
+    if (prof) cudaEventRecord(pe0, g_eigd_stream);
     switch (L.kind) {
       case 0: EIGD_LAUNCH(extend_add_kernel, L.count, 256, 0, h->d, t, f->fronts); break;
       case 1: EIGD_LAUNCH(diag_factor_kernel, L.count, 256, 0, h->d, t, L.kb, f->fronts, f->linv, f->dval, f->dinv, f->amax, f->piv_tol, f->info); break;
@@ -756,6 +765,54 @@ extern "C" int eigd_factor_numeric(eigd_factor* f, int64_t nnz, const double* d_
     }
     EIGD_CHECK_LAUNCH();
   }
+  return 0;
+}
+
+// ---- FP64 tensor-pipe peak of this GPU, measured: every warp of every SM issues independent DMMA chains on register
+// operands (8 accumulator pairs per warp, no memory traffic).  bench.py divides the factorisation's flop rate by it
+// (roofline_fp64_tensor); profiles/ holds the ncu pipe utilisation of trailing_update_kernel next to it.
+__global__ void __launch_bounds__(256) dmma_peak_kernel(int iters, double* __restrict__ sink) {
+  double c[8][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { c[i][0] = 0.0; c[i][1] = 0.0; }
+  double a = 1.0 + 1e-9 * threadIdx.x, b = 1.0 - 1e-9 * threadIdx.x;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dmma_m8n8k4(c[i][0], c[i][1], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+  if (s == 123.456) sink[0] = s;          // keep the chains alive
+}
+
+// -> TFLOP/s (2 * 8 * 8 * 4 flop per warp-level MMA), best of `reps` timed launches on the library's stream
+extern "C" int eigd_dmma_peak(int iters, int reps, double* tflops_out) {
+  int dev = 0, sms = 0;
+  EIGD_CUDA(cudaGetDevice(&dev));
+  EIGD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  double* sink = nullptr;
+  EIGD_CUDA(cudaMalloc((void**)&sink, 8));
+  cudaEvent_t e0, e1;
+  EIGD_CUDA(cudaEventCreate(&e0));
+  EIGD_CUDA(cudaEventCreate(&e1));
+  const int grid = sms * 8, block = 256;
+  double best = 0.0;
+  for (int r = 0; r < reps + 1; ++r) {
+    EIGD_CUDA(cudaEventRecord(e0, g_eigd_stream));
+    EIGD_LAUNCH(dmma_peak_kernel, grid, block, 0, iters, sink);
+    EIGD_CHECK_LAUNCH();
+    EIGD_CUDA(cudaEventRecord(e1, g_eigd_stream));
+    EIGD_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    EIGD_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    const double flops = (double)grid * (block / 32) * (double)iters * 8.0 * 512.0;
+    if (r > 0 && ms > 0.f) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  *tflops_out = best;
   return 0;
 }
 

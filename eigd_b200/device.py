@@ -127,6 +127,19 @@ def solve_timing_end():
     return {k: (int(calls[k]), float(ms[k])) for k in range(33) if calls[k]}
 
 
+_DMMA_PEAK = {}
+
+
+def dmma_peak_tflops():
+    """Measured FP64 tensor-pipe peak (TFLOP/s) of the current device (eigd_dmma_peak; cached per device)."""
+    d = dev()
+    if d not in _DMMA_PEAK:
+        out = ctypes.c_double(0.0)
+        check(_lib.load().eigd_dmma_peak(4096, 3, ctypes.byref(out)), "dmma_peak")
+        _DMMA_PEAK[d] = float(out.value)
+    return _DMMA_PEAK[d]
+
+
 def launch_count():
     return int(_lib.load().eigd_launch_count())
 
@@ -141,6 +154,7 @@ _BIG_COPY = 1 << 20
 
 class _Copy:
     stream = None
+    pending = []        # events of uploads issued straight from the caller's page-locked arrays (see drain_uploads)
 
 
 def _copy_stream():
@@ -198,10 +212,22 @@ def h2d(a):
     out.record_stream(main)
     _stat("h2d issue", t0, a.nbytes)
     if own:
-        t0 = time.perf_counter()
-        ev.synchronize()                            # the caller may overwrite its array once we return
-        _stat("h2d wait (caller's pinned array)", t0, a.nbytes)
+        # the DMA reads the caller's own page-locked array: it must have finished before control returns to the
+        # caller (who may overwrite the array) -- not before this function returns.  The public entry points drain
+        # the list on their way out (drain_uploads), so the host keeps enqueueing kernels meanwhile.
+        _Copy.pending.append(ev)
     return out
+
+
+def drain_uploads():
+    """Wait for the uploads that read the caller's page-locked arrays directly (called by every public entry point
+    before it returns; a no-op when nothing is pending)."""
+    if _Copy.pending:
+        t0 = time.perf_counter()
+        for ev in _Copy.pending:
+            ev.synchronize()
+        _stat("h2d wait (caller's pinned arrays, at API exit)", t0, 0)
+        _Copy.pending.clear()
 
 
 def d2h(t):
@@ -211,6 +237,8 @@ def d2h(t):
         t0 = time.perf_counter()
         out = t.cpu().numpy()
         _stat("d2h small (.cpu, includes waiting for the GPU)", t0, out.nbytes)
+        if t.is_cuda:
+            _Copy.pending.clear()       # the compute stream waited for every earlier upload and has just been drained
         return out
     t0 = time.perf_counter()
     stage = torch.empty_like(t, device="cpu", pin_memory=True)
@@ -223,6 +251,7 @@ def d2h(t):
     t0 = time.perf_counter()
     ev.synchronize()
     _stat("d2h wait (includes waiting for the GPU)", t0, stage.numel() * stage.element_size())
+    _Copy.pending.clear()               # (as above)
     return stage.numpy()
 
 

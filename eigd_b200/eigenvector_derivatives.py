@@ -31,6 +31,20 @@ __all__ = ["SpLuOperator", "add_eig_total_derivative", "eval_adjoint_residual_no
 _SYMBOLIC_CACHE = {}
 
 
+def _public(fn):
+    """Public entry point: uploads issued straight from the caller's page-locked arrays are awaited before control
+    returns to the caller (device.drain_uploads), whatever path the call takes."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        try:
+            return fn(*args, **kwargs)
+        finally:
+            D.drain_uploads()
+    return wrapper
+
+
 def _is_complex_host(M):
     """scipy sparse matrix with complex values (a complex-step operand); device matrices are always real"""
     d = getattr(M, "data", None)
@@ -91,6 +105,7 @@ class SpLuOperator:
     refinement steps per solve (default: 1 if the factorisation met negative or perturbed pivots).
     """
 
+    @_public
     def __init__(self, mat, coords=None, dof_per_node=1, symbolic=None, refine=None, max_rhs=32):
         self.tangent = None
         if isinstance(mat, D.CsrDevice):
@@ -202,6 +217,7 @@ class SpLuOperator:
                 D.col_axpy(X, small_to_dev(np.ones(k)), dX, sign=1.0)
         return X
 
+    @_public
     def _apply(self, x):
         if is_dev(x):
             return self.solve_dev(x)
@@ -311,6 +327,7 @@ def _call_deriv(fn, W_d, V_d, host):
     return fn(to_host(W_d), to_host(V_d))
 
 
+@_public
 def add_eig_total_derivative(lam, Phi, lamb, Phib, psi, dAdx, dBdx, dfdx, adj_corr_data={}, mode="normal",
                              deriv_type="vector"):
     """Reference ``add_eig_total_derivative`` (:33-182): dfdx += sum_i w_i^T (dA/dx) phi_i -/+ ...
@@ -369,6 +386,7 @@ def add_eig_total_derivative(lam, Phi, lamb, Phib, psi, dAdx, dBdx, dfdx, adj_co
 # ------------------------------------------------------------------------------------------
 # residual check -- reference :185-275
 # ------------------------------------------------------------------------------------------
+@_public
 def eval_adjoint_residual_norm(A, B, lam, Phi, Phib, psi, mode="normal", b_ortho=False):
     """Reference :185-275: ||L_i psi_i - b_i||_2 and the B-orthogonality defect, per mode."""
     n, N = A.shape[1], Phi.shape[1]
@@ -443,6 +461,7 @@ def _apply_correction_dev(lam, Phi_d, psi_d, G, eig_atol, mode):
     return data
 
 
+@_public
 def generate_adjoint_correction(lam, Phi, psi, G=None, Phib=None, eig_atol=1e-5, mode="normal"):
     """Reference :303-391.  ``psi`` is corrected in place; returns the repeated-eigenvalue data."""
     _check_mode(mode)
@@ -507,6 +526,7 @@ def _laa_dev(Phib_d, Bd, factor, sigma, lam, V_d, Y, theta, indices, b_ortho, mo
     return factor.solve_dev(Bd.spmm(X))
 
 
+@_public
 def laa(Phib, B, factor, sigma, lam, V, Y, theta, indices, D0=None, b_ortho=False, mode="normal"):
     """Reference ``laa`` (:394-523): Galerkin solution of the adjoint equations in span(V)."""
     _check_mode(mode)
@@ -596,6 +616,7 @@ def _dl_dev(Phib_d, Bd, factor, sigma, lam, Phi_d, indices, V_d, T, Y, theta, ei
     return psi, data
 
 
+@_public
 def dl(Phib, B, factor, sigma, lam, Phi, indices, V, T, Y, theta, eig_atol=1e-5, mode="normal"):
     """Reference ``dl`` (:526-696): reverse-mode differentiation of the un-restarted Lanczos recurrence."""
     _check_mode(mode)
@@ -904,6 +925,7 @@ def _sibk_seq_dev(Phib_d, Ad, Bd, lam, Phi_d, mode, psi_d, sigma, factor, rtol, 
     return G, info
 
 
+@_public
 def sibk(Phib, A, B, lam, Phi, mode="normal", psi=None, sigma=None, factor=None, rtol=1e-10, atol=1e-30,
          eig_atol=1e-5, maxiter=50, bs_target=1, update_guess=False, callback=None, nrestart=2):
     """Reference ``sibk`` (:1052-1328), shift-and-invert block Krylov, with the N per-mode Arnoldi
@@ -976,6 +998,7 @@ def _pcpg_dev(Phib_d, Ad, Bd, lam, Phi_d, mode, psi_d, factor, rtol, atol, maxit
     return G, info, hist
 
 
+@_public
 def pcpg(Phib, A, B, lam, Phi, mode="normal", psi=None, sigma=None, factor=None, rtol=1e-10, atol=1e-30,
          eig_atol=1e-5, maxiter=100, reset=25, callback=None):
     """Reference ``pcpg`` (:699-869): projected preconditioned conjugate gradients, all modes in lock step."""
@@ -1048,6 +1071,7 @@ def _pgmres_dev(Phib_d, Ad, Bd, lam, Phi_d, mode, psi_d, factor, rtol, atol, max
     return G, info, hist
 
 
+@_public
 def pgmres(Phib, A, B, lam, Phi, mode="normal", psi=None, sigma=None, factor=None, rtol=1e-10, atol=1e-30,
            eig_atol=1e-5, maxiter=50, callback=None):
     """Reference ``pgmres`` (:872-1040): right-preconditioned projected GMRES, all modes in lock step."""
@@ -1243,6 +1267,7 @@ class BasicLanczos(_SolverBase):
         self._V_host = np.stack([to_host(v.r) + 1j * to_host(v.t) for v in res["V"]], axis=1)
         return self.lam0, self.Phi
 
+    @_public
     def solve(self, A, B, factor, sigma):
         if _is_complex_host(A) or _is_complex_host(B):
             return self._solve_dual(A, B, factor, sigma)
@@ -1330,15 +1355,18 @@ class BasicLanczos(_SolverBase):
             self._V_host = to_host(self._Vt).T.copy()
         return self._V_host
 
+    @_public
     def solve_adjoint(self, Phib, method="sibk", psi=None, rtol=1e-10, atol=1e-30, lanczos_guess=True, **kwargs):
         """Reference :1652-1797."""
         return self._adjoint(self.lam0, Phib, method, psi, rtol, atol, lanczos_guess, dict(kwargs))
 
+    @_public
     def eval_adjoint_residual_norm(self, Phib, psi, b_ortho=False):
         """Reference :1799-1828."""
         return eval_adjoint_residual_norm(self._Ad, self._Bd, self.lam0, self._phi_dev(), self._phib_dev(Phib), to_dev(psi),
                                           mode=self.mode, b_ortho=b_ortho)
 
+    @_public
     def add_total_derivative(self, lamb, Phib, psi, dAdx, dBdx, dfdx, adj_corr_data={}, deriv_type="vector"):
         """Reference :1830-1870."""
         return add_eig_total_derivative(self.lam0, self._phi_dev(), lamb, self._phib_dev(Phib), to_dev(psi), dAdx, dBdx, dfdx,
@@ -1365,6 +1393,7 @@ class IRAM(_SolverBase):
         self.reference_pairing = False
         self._Phi_d = None
 
+    @_public
     def solve(self, A, B, factor, sigma):
         n = self._common_solve_checks(A, B, factor)
         self.factor, self.A, self.B, self.sigma = factor, A, B, sigma
@@ -1419,6 +1448,7 @@ class IRAM(_SolverBase):
             self._V_host = to_host(self.lanczos_state.Vt).T.copy()
         return self._V_host
 
+    @_public
     def solve_adjoint(self, Phib, method="sibk", psi=None, rtol=1e-10, atol=1e-30, lanczos_guess=True, **kwargs):
         """Reference :1988-2134."""
         if method == "dl":
@@ -1426,11 +1456,13 @@ class IRAM(_SolverBase):
                           "results with a restarted basis; use BasicLanczos.")                # :2039-2043
         return self._adjoint(self.lam, Phib, method, psi, rtol, atol, lanczos_guess, dict(kwargs))
 
+    @_public
     def eval_adjoint_residual_norm(self, Phib, psi, b_ortho=False):
         """Reference :2136-2165."""
         return eval_adjoint_residual_norm(self._Ad, self._Bd, self.lam, self._phi_dev(), self._phib_dev(Phib), to_dev(psi),
                                           mode=self.mode, b_ortho=b_ortho)
 
+    @_public
     def add_total_derivative(self, lamb, Phib, psi, dAdx, dBdx, dfdx, adj_corr_data={}, deriv_type="vector"):
         """Reference :2167-2207."""
         return add_eig_total_derivative(self.lam, self._phi_dev(), lamb, self._phib_dev(Phib), to_dev(psi), dAdx, dBdx, dfdx,

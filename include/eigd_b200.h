@@ -117,6 +117,10 @@ int eigd_factor_create(eigd_symbolic* s, int max_rhs, eigd_factor** out);
 int64_t eigd_factor_workspace_bytes(eigd_symbolic* s, int max_rhs);
 int eigd_factor_create_in(eigd_symbolic* s, int max_rhs, void* d_workspace, int64_t workspace_bytes, eigd_factor** out);
 void eigd_factor_destroy(eigd_factor* f);
+/* measured FP64 tensor-pipe (DMMA, mma.sync.m8n8k4.f64) peak of the current device in TFLOP/s: register-resident
+ * micro-benchmark on all SMs, best of `reps` launches of `iters` x 8 MMAs per warp (denominator of bench.py's
+ * roofline_fp64_tensor) */
+int eigd_dmma_peak(int iters, int reps, double* tflops_out);
 /* numeric factorisation from device CSR values + device assembly map */
 int eigd_factor_numeric(eigd_factor* f, int64_t nnz, const double* d_vals, const int64_t* d_map);
 /* info[0] = #negative pivots (inertia), info[1] = #perturbed pivots, info[2] = #non-finite */
