@@ -764,6 +764,22 @@ extern "C" int eigd_factor_numeric(eigd_factor* f, int64_t nnz, const double* d_
       default: break;
     }
     EIGD_CHECK_LAUNCH();
+    if (prof) {
+      cudaEventRecord(pe1, g_eigd_stream);
+      cudaEventSynchronize(pe1);
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, pe0, pe1);
+      kind_ms[L.kind & 7] += ms;
+      kind_n[L.kind & 7]++;
+    }
+  }
+  if (prof) {
+    static const char* names[8] = {"extend_add", "diag_factor", "trsm", "trailing_update", "inverse_init", "inverse_ca", "inverse_bt", "panel_build"};
+    fprintf(stderr, "[factor prof] n=%d levels=%d:", s->n, s->nlevels);
+    for (int k = 0; k < 8; ++k) fprintf(stderr, " %s %.3f ms / %d;", names[k], kind_ms[k], kind_n[k]);
+    fprintf(stderr, "\n");
+    cudaEventDestroy(pe0);
+    cudaEventDestroy(pe1);
   }
   return 0;
 }
