@@ -404,14 +404,20 @@ class NodeFilter:
     def __init__(self, conn, X, r0=1.0, ftype="spatial", dvmap=None, num_design_vars=None, beta=10.0, eta=0.5,
                  projection=False):
         from scipy import sparse, spatial
-        if ftype != "spatial":
-            raise NotImplementedError("only the spatial (conic) filter is implemented")
+        if ftype not in ("spatial", "helmholtz"):
+            raise ValueError("unknown filter type %r" % ftype)
+        self.ftype = ftype
         self.projection = bool(projection)
         self.beta = 10.0 if beta is None else float(beta)      # reference default (node_filter.py:30-31)
         self.eta = float(eta)
         self.X = np.asarray(X, dtype=np.float64)
         self.nnodes = self.X.shape[0]
         self.r0 = r0
+        self.dvmap = None if dvmap is None else np.asarray(dvmap, dtype=np.int64)
+        self.offset_d = None
+        if ftype == "helmholtz":
+            self._init_helmholtz(conn, r0, num_design_vars)
+            return
         tree = spatial.cKDTree(self.X)
         Dm = tree.sparse_distance_matrix(tree, r0, output_type="coo_matrix")
         w = r0 - Dm.data
@@ -441,7 +447,40 @@ class NodeFilter:
         self.F_d = D.CsrDevice.from_scipy(F)
         self.FT_d = D.CsrDevice.from_scipy(FT)
 
+    def _init_helmholtz(self, conn, r0, num_design_vars):
+        """Helmholtz (PDE) filter of examples/node_filter.py:90-162: rho = A^-1 (B x) with A = r0^2 int grad N . grad N +
+        int N N and B = int N N on the Q4 mesh.  A and B are the unit-material thermal stiffness / capacity matrices of
+        ``Q4Problem`` (assembled by the same gather kernel), A is factored once by the GPU LDL^T (the reference uses
+        scipy's ``factorized``) and applied to one right-hand side per call."""
+        from .eigenvector_derivatives import SpLuOperator
+        prob = Q4Problem(conn, self.X, "thermal", kappa=1.0, density=1.0, heat_capacity=1.0, p=1.0, beta=0.0)
+        prob.set_density(rhoE=np.ones(prob.nelems))
+        K, M = prob.assemble()
+        self._hB = M
+        vals = D.axpby(float(r0) ** 2, K.data, 1.0, M.data)
+        self._hA = SpLuOperator(K.with_values(vals), coords=self.X, dof_per_node=1, max_rhs=1)
+        self._hprob = prob
+        if self.dvmap is None:
+            self.num_design_vars = self.nnodes
+            self._dv_d = self._act_d = None
+        else:
+            dev = D.dev()
+            self.num_design_vars = int(num_design_vars if num_design_vars is not None else self.dvmap.max() + 1)
+            act = self.dvmap >= 0
+            self._dv_d = torch.as_tensor(np.where(act, self.dvmap, 0), device=dev)
+            self._act_d = torch.as_tensor(act, device=dev)
+            self._act_idx = torch.as_tensor(np.nonzero(act)[0], device=dev)
+            self._act_dv = torch.as_tensor(self.dvmap[act], device=dev)
+
+    def _expand_design(self, x_d):
+        if self.dvmap is None:
+            return x_d
+        xn = x_d.index_select(0, self._dv_d)                     # x[dvmap], and x := 1 where dvmap < 0 (:166-168)
+        return torch.where(self._act_d, xn, torch.ones_like(xn))
+
     def _filtered(self, x_d):
+        if self.ftype == "helmholtz":
+            return self._hA.solve_dev(self._hB.spmm(self._expand_design(x_d)))
         rho = self.F_d.spmm(x_d)
         if self.offset_d is not None:
             D.axpby(1.0, rho, 1.0, self.offset_d, out=rho)
@@ -465,4 +504,11 @@ class NodeFilter:
             if x is None:
                 raise ValueError("apply_gradient with projection needs the design x")
             g_d = self._project(self._filtered(to_dev(x)), _contig1(g_d))
+        if self.ftype == "helmholtz":                          # g0 = B^T A^-1 grad (:205-209), then the dv-map scatter (:211-214)
+            g0 = self._hB.spmm(self._hA.solve_dev(_contig1(g_d)))
+            if self.dvmap is not None:
+                out = D.zeros(self.num_design_vars)
+                out.index_add_(0, self._act_dv, g0.index_select(0, self._act_idx))
+                g0 = out
+            return like_input(g0, g)
         return like_input(self.FT_d.spmm(g_d), g)

@@ -19,7 +19,7 @@ import torch
 
 from . import device as D
 from . import fe
-from ._hostdev import is_dev, small_to_dev, to_dev, to_host
+from ._hostdev import is_dev, like_input, small_to_dev, to_dev, to_host
 from .eigenvector_derivatives import IRAM, BasicLanczos, SpLuOperator
 
 
@@ -188,6 +188,45 @@ class NaturalFrequencyAnalysis(_Q4Analysis):
         super().__init__(fltr, conn, X, sigma, N=N, E=E, nu=nu, density=density, p=float(p), rho0_K=rho0_K,
                          ptype_K=ptype_K, q=q, **kw)
 
+    # ---- objective helpers of examples/natural_frequency.py:521-563 -------------------------------------
+    def get_frequencies(self):
+        return np.sqrt(np.asarray(self.lam))
+
+    def add_frequency_derivatives(self, omegab):
+        """lamb_i += omegab_i / (2 sqrt(lam_i))   (:524-529)"""
+        self.lamb += 0.5 * np.asarray(omegab) / np.sqrt(np.asarray(self.lam))
+
+    def _set_rows(self, name):
+        if name not in self.node_sets:
+            raise ValueError("Unrecognized point name")
+        nodes = np.asarray(self.node_sets[name], dtype=np.int64)
+        key = ("rows", name)
+        if key not in self.__dict__.setdefault("_cache", {}):
+            self._cache[key] = (torch.as_tensor(2 * nodes, device=D.dev()), torch.as_tensor(2 * nodes + 1, device=D.dev()))
+        return nodes, self._cache[key]
+
+    def get_point_coefficients(self, name):
+        """Mean position of a node set and the mean modal displacement over it, (3, N) (:531-551)."""
+        nodes, (rx, ry) = self._set_rows(name)
+        weight = 1.0 / len(nodes)
+        x0 = np.zeros(3)
+        x0[0], x0[1] = weight * np.sum(self.X[nodes, 0]), weight * np.sum(self.X[nodes, 1])
+        xcoef = None
+        if self.Q is not None:
+            xcoef = np.zeros((3, self.N))
+            xcoef[0] = weight * to_host(self.Q.index_select(0, rx).sum(dim=0))
+            xcoef[1] = weight * to_host(self.Q.index_select(0, ry).sum(dim=0))
+        return x0, xcoef
+
+    def add_point_derivative(self, name, x0b, xcoefb):
+        """Qb[2 nodes, i] += w xcoefb[0, i], Qb[2 nodes + 1, i] += w xcoefb[1, i]   (:553-563)"""
+        if xcoefb is None:
+            return
+        nodes, (rx, ry) = self._set_rows(name)
+        weight = 1.0 / len(nodes)
+        self.Qb.index_add_(0, rx, small_to_dev(weight * np.asarray(xcoefb)[0][None, :]).expand(len(nodes), self.N).contiguous())
+        self.Qb.index_add_(0, ry, small_to_dev(weight * np.asarray(xcoefb)[1][None, :]).expand(len(nodes), self.N).contiguous())
+
     def add_modal_function_derivative(self, w):
         """Seed of a smooth function f = sum_i (phi_i . w_i)^2 of the flexible modes (used by the tests and
         the bench; the KS minimum-frequency objective of the example is host-side numpy)."""
@@ -195,6 +234,74 @@ class NaturalFrequencyAnalysis(_Q4Analysis):
         val = to_host(D.col_dot(self.Q, w_d))
         D.col_axpy(self.Qb, small_to_dev(2.0 * val), w_d, sign=1.0)
         return float(np.sum(val**2))
+
+
+class MinFreqOpt:
+    """KS-aggregated minimum natural frequency of the structure with a point mass attached at each node set in turn
+    (examples/natural_frequency.py ``MinFreqOpt`` :693-803).  For node set s with modal coefficients c (3 x N) the
+    frequencies of structure + mass are those of the N x N pencil (diag(omega^2), I + m c^T c); the objective is the
+    soft minimum (KS, parameter ks_param) over all sets and modes.  Only N x N host algebra: the n-sized work is the
+    eigensolve and the adjoint of ``topo``."""
+
+    def __init__(self, topo, ks_param=1.0, fixed_mass=1.0):
+        self.topo, self.ks_param, self.fixed_mass = topo, ks_param, fixed_mass
+        self.ks_min = 0.0
+        self.node_sets = topo.node_sets
+        self.coef, self.coefb, self.omega, self.omegab = {}, {}, None, None
+
+    def initialize(self, store=False):
+        self.topo.initialize(store)
+        self.omega = self.topo.get_frequencies()
+        self.coef = {name: self.topo.get_point_coefficients(name)[1] for name in self.node_sets}
+        self.ks_min, self.omegab, self.coefb = self._eval_min_frequency(self.omega, self.coef, self.ks_param, self.fixed_mass)
+
+    def initialize_adjoint(self):
+        self.topo.initialize_adjoint()
+
+    def finalize_adjoint(self):
+        self.topo.add_frequency_derivatives(self.omegab)
+        for name in self.node_sets:
+            self.topo.add_point_derivative(name, None, self.coefb[name])
+        self.topo.finalize_adjoint()
+
+    def get_min_frequency(self):
+        return self.ks_min
+
+    @staticmethod
+    def _soft_min(vals, p):
+        lo = np.min(vals)
+        e = np.exp(-p * (vals - lo))
+        return lo - np.log(np.sum(e)) / p, e / np.sum(e)
+
+    def _eval_min_frequency(self, omega, xcoef, ks_param=30.0, fixed_mass=1.0):
+        from scipy.linalg import eigh
+        N = len(omega)
+        names = list(xcoef)
+        pencil = {}
+        inner = {}
+        for name in names:
+            c0 = xcoef[name]
+            lam0, Q0 = eigh(np.diag(omega ** 2), np.eye(N) + fixed_mass * (c0.T @ c0))
+            om0 = np.sqrt(lam0)
+            pencil[name] = (om0, Q0)
+            inner[name] = self._soft_min(om0, ks_param)                      # (KS of this set, weights over its modes)
+        # outer soft minimum over the sets, anchored at min(omega, KS values) as the reference does (:757-768)
+        vals = np.array([inner[name][0] for name in names])
+        anchor = min(np.min(omega), np.min(vals)) if len(vals) else np.min(omega)
+        e = np.exp(-ks_param * (vals - anchor))
+        ks = anchor - np.log(np.sum(e)) / ks_param
+        wset = e / np.sum(e)
+        omegab = np.zeros(N)
+        xcoefb = {}
+        for name, ws in zip(names, wset):
+            c0 = xcoef[name]
+            om0, Q0 = pencil[name]
+            wb = 0.5 * inner[name][1] * ws / om0                             # d ks / d lam0_i
+            omegab += 2.0 * omega * np.einsum("ik,k,ik->i", Q0, wb, Q0)      # through K0 = diag(omega^2)
+            # through M0 = I + m c^T c:  d lam0_i = -lam0_i q_i^T dM0 q_i
+            sc = 2.0 * wb * fixed_mass * om0 ** 2
+            xcoefb[name] = -(c0 @ Q0) * sc[None, :] @ Q0.T
+        return ks, omegab, xcoefb
 
 
 def make_thermal_model(nx=128, ny=128, Lx=1.0, Ly=1.0, rfact=4.0, **kwargs):
@@ -400,6 +507,38 @@ class BucklingTopologyAnalysis:
         else:
             self.lamb -= hb * rho * eta * (a + b) * (qn * qn - h)
         return h
+
+    def eval_ks_buckling(self, ks_rho=160.0):
+        """KS maximum of mu_i = 1 / BLF_i (:641-646)."""
+        mu = 1.0 / np.asarray(self.BLF)
+        c = np.max(mu)
+        return float(c + np.log(np.sum(np.exp(ks_rho * (mu - c)))) / ks_rho)
+
+    def eval_ks_buckling_derivative(self, ks_rho=160.0):
+        """Design gradient of ``eval_ks_buckling`` (:648-700, tensor form): eigenvalue sensitivities only (no eigenvector
+        adjoint), with the fundamental-path adjoint K_r a_r = -(dG/du)_r.  Everything stays in HBM; returns the
+        gradient in the flavour of ``self.x``."""
+        t0 = _now()
+        pr = self.prob
+        mu = 1.0 / np.asarray(self.BLF)
+        eta = np.exp(ks_rho * (mu - np.max(mu)))
+        eta /= np.sum(eta)
+        Q = self.Qr
+        etaQ = Q.clone()
+        D.col_scale(etaQ, small_to_dev(eta), mode=0)
+        etamuQ = Q.clone()
+        D.col_scale(etamuQ, small_to_dev(eta * mu), mode=0)
+        dKdx = pr.dKdx.device_call(etamuQ, Q)                               # per element
+        dGdu = pr.dGdu.device_call(etaQ, Q)                                 # full dof vector
+        adj_r = self.Kfact.solve_dev(pr.reduce_vector(dGdu))
+        adj = pr.full_vector(adj_r)                                         # = -adjoint of the reference (:689-690)
+        dGdx = pr.dGdx.device_call(etaQ, Q)
+        dfde = D.axpby(-1.0, dGdx, -1.0, dKdx)                              # -(dGdx + dKdx) ...
+        D.axpby(1.0, dfde, 1.0, pr.dK_single(adj, self.u_d), out=dfde)      # ... - dK(adj_ref, u) = + dK(adj, u)
+        dfdrho = pr.scatter_to_nodes(dfde)
+        g = self.fltr.apply_gradient(dfdrho, self.x_d)
+        self.profile["total derivative time"] = self.profile.get("total derivative time", 0.0) + (_now() - t0)
+        return like_input(g, self.x)
 
     # ---- reverse (:866-982) -------------------------------------------------------------------------
     def finalize_adjoint(self):

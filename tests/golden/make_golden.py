@@ -177,6 +177,53 @@ def buckling_case(solver_type="BasicLanczos", methods=("sibk", "pcpg"), nx=16, n
     return out
 
 
+def objectives_case(seed=1):
+    """The objective-side pieces of the examples, run with the unmodified reference drivers:
+      * MinFreqOpt of examples/natural_frequency.py (:693-803): KS minimum frequency with point masses, full gradient;
+      * eval_ks_buckling / eval_ks_buckling_derivative of examples/buckling.py (:641-700);
+      * the Helmholtz (PDE) filter of examples/node_filter.py (:90-162, 164-217) with a design-variable map."""
+    out = {}
+    nf = rl.load_example("natural_frequency")
+    np.random.seed(seed)
+    nx, ny, N = 40, 20, 5
+    topo = nf.make_model(nx=nx, ny=ny, Lx=2.0, Ly=1.0, N=N, solver_type="IRAM", adjoint_method="sibk",
+                         adjoint_options=dict(SIBK), rtol=1e-12, deriv_type="tensor")
+    topo.x[:] = np.random.uniform(0.3, 1.0, topo.x.shape)
+    opt = nf.MinFreqOpt(topo, ks_param=30.0, fixed_mass=10.0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        opt.initialize()
+        opt.initialize_adjoint()
+        opt.finalize_adjoint()
+    out.update(dict(mf_nx=nx, mf_ny=ny, mf_N=N, mf_x=topo.x.copy(), mf_ks=opt.get_min_frequency(), mf_omega=opt.omega.copy(),
+                    mf_omegab=opt.omegab.copy(), mf_xb=topo.xb.copy(), mf_lamb=topo.lamb.copy()))
+    bk = rl.load_example("buckling")
+    np.random.seed(seed)
+    bnx, bny, bN = 16, 32, 5
+    topo = bk.make_model(nx=bnx, ny=bny, N=bN, m=60, sigma=3.0, solver_type="IRAM", adjoint_method="sibk",
+                         adjoint_options=dict(SIBK), rtol=1e-12, deriv_type="tensor")
+    topo.x[:] = np.random.uniform(0.3, 1.0, topo.x.shape)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        topo.initialize()
+        ks = topo.eval_ks_buckling(ks_rho=160.0)
+        dks = topo.eval_ks_buckling_derivative(ks_rho=160.0)
+    out.update(dict(ks_nx=bnx, ks_ny=bny, ks_N=bN, ks_x=topo.x.copy(), ks_value=ks, ks_grad=np.asarray(dks).copy(),
+                    ks_BLF=np.asarray(topo.BLF).copy()))
+    nfl = rl.load_example("node_filter")
+    conn, X = topo.conn, topo.X
+    dvmap, ndv = topo.fltr.dvmap, topo.fltr.num_design_vars
+    hf = nfl.NodeFilter(conn, X, r0=0.12, ftype="helmholtz", dvmap=dvmap, num_design_vars=ndv, projection=True, beta=6.0, eta=0.4)
+    xh = np.random.default_rng(seed).uniform(0.2, 1.0, ndv)
+    gh = np.random.default_rng(seed + 1).normal(size=X.shape[0])
+    out.update(dict(hf_conn=conn, hf_X=X, hf_dvmap=np.asarray(dvmap), hf_ndv=ndv, hf_r0=0.12, hf_x=xh, hf_g=gh,
+                    hf_rho=hf.apply(xh.copy()), hf_grad=hf.apply_gradient(gh, xh.copy())))
+    hf0 = nfl.NodeFilter(conn, X, r0=0.12, ftype="helmholtz")
+    x0 = np.random.default_rng(seed + 2).uniform(0.2, 1.0, X.shape[0])
+    out.update(dict(hf0_x=x0, hf0_rho=hf0.apply(x0.copy()), hf0_grad=hf0.apply_gradient(gh, x0.copy())))
+    return out
+
+
 def shell_case(nx=16, ny=14, ncx=4, ncy=3, N=6, m=30, omega0=10.0, seed=5):
     """The flow of examples/crm.py (:212-370) -- IRAM, sibk, modal compliance with f[1::6] = 1, add_eig_total_derivative in
     its default per-mode "vector" form -- with the UNMODIFIED reference solvers on host matrices of the synthetic shell
@@ -231,6 +278,7 @@ if __name__ == "__main__":
         "nf_iram": nf_case,
         "buckling_basiclanczos": buckling_case,
         "shell_iram": shell_case,
+        "objectives": objectives_case,
     }
     only = set(sys.argv[1:])
     for name, fn in cases.items():
