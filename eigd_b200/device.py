@@ -544,6 +544,16 @@ def pattern_key(indptr, indices, extra=b""):
     return h.hexdigest()
 
 
+def _same_ints(a, b):
+    """Full element-wise equality of two contiguous int32 arrays (torch's vectorised compare: about a third of the
+    time of numpy.array_equal at 9 MB, no temporary)."""
+    if a.shape != b.shape:
+        return False
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")            # read-only numpy arrays: we only read
+        return bool(torch.equal(torch.from_numpy(a), torch.from_numpy(b)))
+
+
 class PatternCache:
     """Device copies of CSR structures (indptr, indices), shared by every matrix with that pattern.
 
@@ -566,7 +576,7 @@ class PatternCache:
         """-> (entry id, device indptr, device indices, fresh); arrays must be int32, contiguous, sorted rows."""
         fp = cls._fingerprint(indptr, indices)
         for ent in cls._entries.get(fp, []):
-            if np.array_equal(ent[1], indptr) and np.array_equal(ent[2], indices):
+            if _same_ints(ent[1], indptr) and _same_ints(ent[2], indices):
                 return ent[0], ent[3], ent[4], False
         if sum(len(v) for v in cls._entries.values()) > 16:
             cls._entries.clear()

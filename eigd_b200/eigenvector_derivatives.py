@@ -149,37 +149,74 @@ class SpLuOperator:
             symbolic = (symbolic, symbolic.assembly_map_device(csr.indptr, csr.indices))
         self.symbolic, self._amap = symbolic
         self.lu = D.Factor(self.symbolic, max_rhs=max_rhs).numeric(csr.data, self._amap)
-        self.info = self.lu.info()
-        if self.info["non_finite"]:
+        # The factorisation is now queued on the device.  Its pivot statistics (inertia, perturbed pivots) and the choice
+        # of the refinement depth need a read-back, i.e. a wait for the whole factorisation: that is deferred to the first
+        # use (``info`` / ``refine`` / the first solve), so that the caller's next host-side steps -- typically the
+        # upload and verification of K and M in ``solve`` -- overlap with it instead of idling behind it.
+        self._refine_request = refine
+        self._state = None
+
+    def _finish(self):
+        if self._state is not None:
+            return
+        self._state = {"info": None, "refine": 0, "probe": None, "probe_refined": None}
+        st = self._state
+        st["info"] = info = self.lu.info()
+        if info["non_finite"]:
             raise RuntimeError("SpLuOperator: non-finite pivots in the LDL^T factorisation (singular shifted matrix?)")
-        self.probe = self.probe_refined = None
+        refine = self._refine_request
         if refine is None:
-            if self.info["perturbed_pivots"]:
+            if info["perturbed_pivots"]:
                 refine = 1
-            elif self.info["negative_pivots"]:
+            elif info["negative_pivots"]:
                 # indefinite but unperturbed (e.g. K + sigma G above the first buckling load): LDL^T without
                 # pivoting may or may not have lost accuracy -- measure it once on a probe right-hand side and keep
                 # the refinement step unless the plain solve is already at rounding level.  (Measured at C3: probe
                 # 3e-11; dropping the refinement inside the adjoint Krylov solvers alone moved the gradient norm by
                 # 5e-4 relative -- the modes next to the shift amplify the operator error -- so it stays.)
-                self.probe = self._probe_residual()
-                refine = 0 if self.probe < 1e-13 else 1
+                st["probe"] = self._probe_residual()
+                refine = 0 if st["probe"] < 1e-13 else 1
             else:
                 refine = 0
-        self.refine = int(refine)
-        if self.refine and (self.info["perturbed_pivots"] or self.info["negative_pivots"]):
+        st["refine"] = int(refine)
+        if st["refine"] and (info["perturbed_pivots"] or info["negative_pivots"]):
             # static pivoting is only as good as the refined solve it leaves behind: measure that, iterate the
             # refinement to tolerance if one step is not enough, and say so loudly if it cannot be reached
             # (a shift that sits on an eigenvalue; the reference's partially pivoted LU would lose accuracy there too)
-            self.probe_refined = self._probe_residual(refined=True)
-            while self.probe_refined > 1e-10 and self.refine < 4:
-                self.refine += 1
-                self.probe_refined = self._probe_residual(refined=True)
-            if not self.probe_refined <= 1e-8:
+            st["probe_refined"] = self._probe_residual(refined=True)
+            while st["probe_refined"] > 1e-10 and st["refine"] < 4:
+                st["refine"] += 1
+                st["probe_refined"] = self._probe_residual(refined=True)
+            if not st["probe_refined"] <= 1e-8:
                 warnings.warn("SpLuOperator: the LDL^T factorisation of the shifted matrix is inaccurate (relative residual "
                               "%.1e after %d refinement steps, %d perturbed and %d negative pivots); move the shift away "
-                              "from the spectrum" % (self.probe_refined, self.refine, self.info["perturbed_pivots"],
-                                                     self.info["negative_pivots"]))
+                              "from the spectrum" % (st["probe_refined"], st["refine"], info["perturbed_pivots"],
+                                                     info["negative_pivots"]))
+
+    @property
+    def info(self):
+        self._finish()
+        return self._state["info"]
+
+    @property
+    def refine(self):
+        self._finish()
+        return self._state["refine"]
+
+    @refine.setter
+    def refine(self, value):
+        self._finish()
+        self._state["refine"] = int(value)
+
+    @property
+    def probe(self):
+        self._finish()
+        return self._state["probe"]
+
+    @property
+    def probe_refined(self):
+        self._finish()
+        return self._state["probe_refined"]
 
     def _probe_residual(self, refined=False):
         """max |b - mat x| / max |b| of one solve (plain LDL^T sweep, or the refined solve every caller gets) with a
