@@ -38,9 +38,15 @@ __device__ unsigned int g_block_ticket = 0;
 // time; per-warp partial sums accumulate in shared memory, per-CTA partials go to `partial`, the last CTA to finish
 // (ticket) adds them in a fixed order -- bitwise reproducible, one launch.
 template <int P>
+__device__ void block_chol(const double* __restrict__ G, double* __restrict__ Rinv, double* __restrict__ Racc, int pass);
+
+// chol_pass >= 0 (Gram-matrix call, j == P): the last CTA also factors the P x P result (block_chol) -- one launch less
+// per Cholesky-QR pass.
+template <int P>
 __global__ void __launch_bounds__(BK_THREADS)
 block_dots_kernel(int64_t n, int j, const double* __restrict__ Vb, int64_t ldv, const double* __restrict__ W, int64_t ldw,
-                  double* __restrict__ partial, double* __restrict__ out, unsigned int* __restrict__ ticket) {
+                  double* __restrict__ partial, double* __restrict__ out, unsigned int* __restrict__ ticket, int chol_pass,
+                  double* __restrict__ Rinv, double* __restrict__ Racc) {
   extern __shared__ double red[];                // [BK_THREADS / 32][j * P]
   __shared__ bool last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -102,15 +108,22 @@ block_dots_kernel(int64_t n, int j, const double* __restrict__ Vb, int64_t ldv, 
     if (lane == 0) out[e] = s;
   }
   if (tid == 0) *ticket = 0u;
+  if (chol_pass >= 0) {
+    __syncthreads();
+    if (tid == 0) block_chol<P>(out, Rinv, Racc, chol_pass);
+  }
 }
 
 // W[c][i] += sign * sum_a H[a * P + c] * Vb[a][i]
+// H1 / Aout / jblk (second Gram-Schmidt pass only, else NULL): CTA 0 also writes the diagonal block of the projected
+// operator, Aout = (H1 + H)[jblk : jblk + P].
 template <int P>
 __global__ void __launch_bounds__(BK_THREADS)
 block_axpy_kernel(int64_t n, int j, const double* __restrict__ Vb, int64_t ldv, const double* __restrict__ H, double sign,
-                  double* __restrict__ W, int64_t ldw) {
+                  double* __restrict__ W, int64_t ldw, const double* __restrict__ H1, double* __restrict__ Aout, int jblk) {
   extern __shared__ double hs[];                 // [j * P]
   const int tid = threadIdx.x;
+  if (Aout && blockIdx.x == 0 && tid < P * P) Aout[tid] = H1[jblk * P + tid] + H[jblk * P + tid];
   for (int e = tid; e < j * P; e += BK_THREADS) hs[e] = sign * H[e];
   __syncthreads();
   for (int64_t c0 = (int64_t)blockIdx.x * BK_CHUNK; c0 < n; c0 += (int64_t)gridDim.x * BK_CHUNK) {
@@ -159,8 +172,7 @@ block_axpy_kernel(int64_t n, int j, const double* __restrict__ Vb, int64_t ldv, 
 // row-major) for the scaling kernel and accumulates Racc <- R * Racc (Racc = identity on the first pass: pass 0).
 // A non-positive pivot (rank-deficient block: breakdown) is flagged by NaNs, which the host checks once per cycle.
 template <int P>
-__global__ void block_chol_kernel(const double* __restrict__ G, double* __restrict__ Rinv, double* __restrict__ Racc, int pass) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__device__ void block_chol(const double* __restrict__ G, double* __restrict__ Rinv, double* __restrict__ Racc, int pass) {
   double R[P][P], X[P][P];
 #pragma unroll
   for (int a = 0; a < P; ++a)
@@ -239,13 +251,6 @@ block_scale_kernel(int64_t n, const double* __restrict__ Rinv, double* __restric
   }
 }
 
-// A_j = (H1 + H2)[j : j + P] (P x P diagonal block of the projected operator)
-__global__ void block_collect_kernel(int P, int j, const double* __restrict__ H1, const double* __restrict__ H2,
-                                     double* __restrict__ Aout) {
-  const int e = threadIdx.x;
-  if (e < P * P) Aout[e] = H1[j * P + e] + H2[j * P + e];
-}
-
 // r = b - r for P strided vectors; x += dx
 __global__ void block_sub_from_kernel(int64_t n, int P, const double* __restrict__ b, int64_t ldb, double* __restrict__ r, int64_t ldr) {
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n * P; e += (int64_t)gridDim.x * blockDim.x) {
@@ -268,7 +273,8 @@ inline int ew_grid(int64_t n) {
 }
 
 template <int P>
-int dots(int64_t n, int j, const double* Vb, int64_t ldv, const double* W, int64_t ldw, double* out, double* work) {
+int dots(int64_t n, int j, const double* Vb, int64_t ldv, const double* W, int64_t ldw, double* out, double* work,
+         int chol_pass = -1, double* Rinv = nullptr, double* Racc = nullptr) {
   unsigned int* ticket = nullptr;
   EIGD_CUDA(cudaGetSymbolAddress((void**)&ticket, g_block_ticket));
   int64_t want = (n + BK_CHUNK - 1) / BK_CHUNK;
@@ -276,16 +282,17 @@ int dots(int64_t n, int j, const double* Vb, int64_t ldv, const double* W, int64
   int grid = (int)(want < cap ? want : cap);
   if (grid < 1) { eigd_set_error("block_dots: workspace too small"); return 8; }
   const size_t smem = (size_t)(BK_THREADS / 32) * j * P * sizeof(double);
-  EIGD_LAUNCH(block_dots_kernel<P>, grid, BK_THREADS, smem, n, j, Vb, ldv, W, ldw, work, out, ticket);
+  EIGD_LAUNCH(block_dots_kernel<P>, grid, BK_THREADS, smem, n, j, Vb, ldv, W, ldw, work, out, ticket, chol_pass, Rinv, Racc);
   EIGD_CHECK_LAUNCH();
   return 0;
 }
 
 template <int P>
-int axpy(int64_t n, int j, const double* Vb, int64_t ldv, const double* H, double sign, double* W, int64_t ldw) {
+int axpy(int64_t n, int j, const double* Vb, int64_t ldv, const double* H, double sign, double* W, int64_t ldw,
+         const double* H1 = nullptr, double* Aout = nullptr, int jblk = 0) {
   int64_t want = (n + BK_CHUNK - 1) / BK_CHUNK;
   int grid = (int)(want < 148 * 16 ? want : 148 * 16);
-  EIGD_LAUNCH(block_axpy_kernel<P>, grid, BK_THREADS, (size_t)j * P * sizeof(double), n, j, Vb, ldv, H, sign, W, ldw);
+  EIGD_LAUNCH(block_axpy_kernel<P>, grid, BK_THREADS, (size_t)j * P * sizeof(double), n, j, Vb, ldv, H, sign, W, ldw, H1, Aout, jblk);
   EIGD_CHECK_LAUNCH();
   return 0;
 }
@@ -298,9 +305,7 @@ int cholqr2(int64_t n, double* W, double* BW, int64_t ld, double* Racc, double* 
   double* Rinv = scratch + P * P;
   int rc;
   for (int pass = 0; pass < 2; ++pass) {
-    if ((rc = dots<P>(n, P, BW, ld, W, ld, G, work))) return rc;              // G[a * P + c] = BW_a . W_c
-    EIGD_LAUNCH(block_chol_kernel<P>, 1, 32, 0, G, Rinv, Racc, pass);
-    EIGD_CHECK_LAUNCH();
+    if ((rc = dots<P>(n, P, BW, ld, W, ld, G, work, pass, Rinv, Racc))) return rc;   // G = BW^T W, factored by the last CTA
     EIGD_LAUNCH(block_scale_kernel<P>, ew_grid(n), 256, 0, n, Rinv, W, BW, ld);
     EIGD_CHECK_LAUNCH();
   }
@@ -333,9 +338,7 @@ int extend(eigd_factor* f, int refine, int n, const int* mp, const int* mi, cons
     if ((rc = dots<P>(n, m, BV, ld, W, ld, H1, work))) return rc;
     if ((rc = axpy<P>(n, m, V, ld, H1, -1.0, W, ld))) return rc;
     if ((rc = dots<P>(n, m, BV, ld, W, ld, H2, work))) return rc;
-    if ((rc = axpy<P>(n, m, V, ld, H2, -1.0, W, ld))) return rc;
-    EIGD_LAUNCH(block_collect_kernel, 1, 32, 0, P, j, H1, H2, Ablk + (int64_t)step * P * P);
-    EIGD_CHECK_LAUNCH();
+    if ((rc = axpy<P>(n, m, V, ld, H2, -1.0, W, ld, H1, Ablk + (int64_t)step * P * P, j))) return rc;
     // BW = B W, then orthonormalise the block
     if ((rc = eigd_csr_spmm(n, bp, bi, bv, W, 1, ld, BW, 1, ld, P, 1.0, 0.0))) return rc;
     if ((rc = cholqr2<P>(n, W, BW, ld, Rblk + (int64_t)step * P * P, scratch, work))) return rc;

@@ -343,6 +343,61 @@ __device__ __forceinline__ void tile_store(const SolveArgs& a, int dir, const Ti
   }
 }
 
+// The index / scaling operands of tile_store, requested BEFORE the tile waits for its dependencies (level phases): the
+// D^-1 entry, the parent row position or the original index of the output then sit in registers when the sums are
+// ready, instead of adding a dependent look-up (an L2 or DRAM round trip) between the last FMA and the stores.
+struct StoreOps {
+  double di;
+  int64_t dst;
+};
+template <int TH>
+__device__ __forceinline__ StoreOps tile_store_request(const SolveArgs& a, int dir, const TileRec& tr, int lane) {
+  StoreOps o;
+  o.di = 0.0;
+  o.dst = 0;
+  const int nc = tr.nc, f = tr.nc + tr.nb;
+  const int out = tr.tile * TH + lane;
+  if (TH < 32 && lane >= TH) return o;
+  if (dir == 0) {
+    if (out < nc) o.di = __ldg(&a.dinv[tr.first + out]);
+    else if (out < f) {
+      const int slab = (int)((tr.link >> LINK_SLAB_SHIFT) & 0xff);
+      if (slab < 2) o.dst = slab * a.slab_stride + (tr.link & LINK_WOFF_MASK) + __ldg(&a.rel[tr.row_off + out - nc]);
+      else o.dst = 2 * a.slab_stride + tr.w_off + out;
+    }
+  } else if (out < nc) {
+    o.dst = (int64_t)__ldg(&a.perm[tr.first + out]) * a.xrs;
+  }
+  return o;
+}
+template <int KT, int TH>
+__device__ __forceinline__ void tile_store_with(const SolveArgs& a, int dir, const TileRec& tr, int lane, const double* acc,
+                                                const StoreOps& o) {
+  const int k = a.k;
+  const int nc = tr.nc, f = tr.nc + tr.nb;
+  const int out = tr.tile * TH + lane;
+  if (TH < 32 && lane >= TH) return;
+  if (dir == 0) {
+    if (out < nc) {
+      double* y = a.ybuf + (int64_t)(tr.first + out) * k;
+#pragma unroll
+      for (int r = 0; r < KT; ++r)
+        if (r < k) y[r] = o.di * acc[r];
+    } else if (out < f) {
+      double* w = a.wbuf + o.dst;
+#pragma unroll
+      for (int r = 0; r < KT; ++r)
+        if (r < k) w[(int64_t)r * a.sumf] = acc[r];
+    }
+  } else if (out < nc) {
+    double* xp = a.xperm + (int64_t)(tr.first + out) * k;
+    double* xo = a.X + o.dst;
+#pragma unroll
+    for (int r = 0; r < KT; ++r)
+      if (r < k) { xp[r] = acc[r]; xo[(int64_t)r * a.xcs] = acc[r]; }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // FRONT MODE of the subtree phases.  Below the cut the fronts are small (nc ~ 4 - 30 pivot columns, f ~ 20 - 110
 // rows: a 2 - 10 KB panel) and there are thousands of them per SM; with one warp tile per 32 outputs the solve
@@ -793,6 +848,9 @@ __device__ __forceinline__ void level_phase(const SolveArgs& a, const PhaseRec& 
     dw.epoch = a.epoch;
     dw.pending = false;
     dw.td.self = 0;
+    StoreOps sto;
+    sto.di = 0.0;
+    sto.dst = 0;
     if (have) {
       int4 d0, d1;
       if (have_next && ct == (int)blockIdx.x) {
@@ -808,6 +866,7 @@ __device__ __forceinline__ void level_phase(const SolveArgs& a, const PhaseRec& 
       dw.td.self = d0.x; dw.td.ndep = d0.y; dw.td.d0 = d0.z; dw.td.n0 = d0.w;
       dw.td.d1 = d1.x; dw.td.n1 = d1.y; dw.td.ovf = d1.z; dw.td.pad = 0;
       dw.pending = dw.td.ndep > 0;
+      if (KT <= 2 && slice == 0) sto = tile_store_request<TH>(a, dir, tr, lane);      // (costs registers: single / pair solves only)
       const bool tr_on = a.trace && blockIdx.x == 0 && ct == 0 && threadIdx.x == 0;
       if (tr_on) a.trace[8 * p + 0] = clock64();
       if (a.trace) {              // trace build of the chain: wait first so that the segments separate
@@ -818,18 +877,35 @@ __device__ __forceinline__ void level_phase(const SolveArgs& a, const PhaseRec& 
       if (tr_on) a.trace[8 * p + 2] = clock64();
     }
     if (ws > 1) {
+      // partial sums of the ws slices meet in shared memory; the slice-0 warp adds them in a FIXED order (bitwise
+      // reproducible), four independent chains at a time so that the shared-memory latencies overlap
 #pragma unroll
       for (int r = 0; r < KT; ++r) part[(warp * KT + r) * 32 + lane] = acc[r];
       __syncthreads();
-      if (have && slice == 0)
+      if (have && slice == 0 && KT > 2) {
         for (int s = 1; s < ws; ++s)
 #pragma unroll
           for (int r = 0; r < KT; ++r) acc[r] += part[((warp + s) * KT + r) * 32 + lane];
+      }
+      if (have && slice == 0 && KT <= 2) {
+#pragma unroll
+        for (int r = 0; r < KT; ++r) {
+          double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+          for (int s = 1; s < ws; s += 4) {
+            p0 += part[((warp + s) * KT + r) * 32 + lane];
+            if (s + 1 < ws) p1 += part[((warp + s + 1) * KT + r) * 32 + lane];
+            if (s + 2 < ws) p2 += part[((warp + s + 2) * KT + r) * 32 + lane];
+            if (s + 3 < ws) p3 += part[((warp + s + 3) * KT + r) * 32 + lane];
+          }
+          acc[r] += (p0 + p1) + (p2 + p3);
+        }
+      }
     }
     const bool tr_on2 = a.trace && blockIdx.x == 0 && ct == 0 && threadIdx.x == 0;
     if (tr_on2) a.trace[8 * p + 3] = clock64();
     if (have && slice == 0) {
-      tile_store<KT, TH>(a, dir, tr, lane, acc);
+      if (KT <= 2) tile_store_with<KT, TH>(a, dir, tr, lane, acc, sto);
+      else tile_store<KT, TH>(a, dir, tr, lane, acc);
       if (tr_on2) a.trace[8 * p + 4] = clock64();
       signal_done(a.cnt + dw.td.self);
       if (tr_on2) a.trace[8 * p + 5] = clock64();
