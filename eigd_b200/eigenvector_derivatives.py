@@ -1280,8 +1280,13 @@ class BasicLanczos(_SolverBase):
             raise NotImplementedError("complex-step operands are implemented for ortho_type='full'")
         if getattr(factor, "tangent", None) is None:
             raise ValueError("complex A, B need a SpLuOperator built from the complex shifted matrix")
-        z = lambda M: (dual.split_csr(M) if dual.is_complex_matrix(M) else
-                       (as_csr_device(M), as_csr_device(M).with_values(D.zeros(as_csr_device(M).nnz))))
+        def z(M):
+            if isinstance(M, tuple):                     # (value, tangent) CsrDevice pair prepared on the device (topo drivers)
+                return M
+            if dual.is_complex_matrix(M):
+                return dual.split_csr(M)
+            Md = as_csr_device(M)
+            return Md, Md.with_values(D.zeros(Md.nnz))
         (Ar, At), (Br, Bt) = z(A), z(B)
         self.A, self.B, self.factor, self.sigma = A, B, factor, sigma
         self._Ad, self._Bd = Ar, Br
@@ -1306,7 +1311,7 @@ class BasicLanczos(_SolverBase):
 
     @_public
     def solve(self, A, B, factor, sigma):
-        if _is_complex_host(A) or _is_complex_host(B):
+        if _is_complex_host(A) or _is_complex_host(B) or isinstance(A, tuple) or isinstance(B, tuple):
             return self._solve_dual(A, B, factor, sigma)
         n = self._common_solve_checks(A, B, factor)
         self.A, self.B, self.factor, self.sigma = A, B, factor, sigma

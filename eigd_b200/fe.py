@@ -174,6 +174,21 @@ class Q4Problem:
                                             _ptr(self.dm_d)), "q4_material")
         return self.rhoE_d
 
+    def assemble_tangent(self, rho_t):
+        """Directional derivative of (K, M) along the nodal density direction ``rho_t`` (device, (nnodes,)), on the same
+        pattern: the assembly kernel with the material factors replaced by (dk/drho_e) rho_e', (dm/drho_e) rho_e'.
+        Used by the dual-number (complex-step) mode of the drivers."""
+        lib = _lib.load()
+        rhoEt, s1, s2, s3, s4 = (D.empty(self.nelems) for _ in range(5))
+        # element mean of the nodal direction (the material outputs of this call are scratch)
+        _lib.check(lib.eigd_q4_material(self.law, self.nelems, _ptr(self.conn_d), _ptr(to_dev(rho_t)), self._par_c, _ptr(rhoEt),
+                                        _ptr(s1), _ptr(s2), _ptr(s3), _ptr(s4)), "q4_material")
+        kt, mt = self.dk_d * rhoEt, self.dm_d * rhoEt
+        Kv, Mv = D.empty(self.nnz), D.empty(self.nnz)
+        D.q4_assemble(self.kid, self.conn_d, self.xy_d, kt, mt, self.cmat6_d, self.src_ptr_d, self.src_d, self.nnz, Kv, Mv)
+        shape = (self.ndof, self.ndof)
+        return (D.CsrDevice(self.indptr_d, self.indices_d, Kv, shape), D.CsrDevice(self.indptr_d, self.indices_d, Mv, shape))
+
     # ---- assembly -------------------------------------------------------------------------------
     def assemble(self):
         """K(rho), M(rho) as CsrDevice sharing one pattern (values computed in gather form)."""
@@ -491,6 +506,18 @@ class NodeFilter:
         _lib.check(_lib.load().eigd_filter_project(rho.shape[0], self.beta, self.eta, _ptr(rho), _ptr(g), _ptr(out)),
                    "filter_project")
         return out
+
+    def apply_tangent(self, x, xt):
+        """Directional derivative of ``apply`` at x along xt (dual-number mode of the drivers)."""
+        x_d, xt_d = to_dev(x), to_dev(xt)
+        if self.ftype == "helmholtz":
+            xt_n = xt_d if self.dvmap is None else torch.where(self._act_d, xt_d.index_select(0, self._dv_d), torch.zeros_like(self._dv_d, dtype=xt_d.dtype))
+            rt = self._hA.solve_dev(self._hB.spmm(xt_n))
+        else:
+            rt = self.F_d.spmm(xt_d)                       # the constant offset of the dv-map has no derivative
+        if self.projection:
+            rt = self._project(self._filtered(x_d), _contig1(rt))
+        return rt
 
     def apply(self, x):
         rho = self._filtered(to_dev(x))

@@ -96,10 +96,46 @@ class _Q4Analysis:
     def initialize(self, store=False, x=None):
         if x is not None:
             self.x = x
+        if not is_dev(self.x) and np.iscomplexobj(self.x):
+            return self._initialize_dual(store)
         self.x_d = to_dev(self.x)
         self.rho = self.fltr.apply(self.x_d)
         self.rhoE = self.prob.set_density(rho=self.rho)
         self.lam, self.Q = self.solve_eigenvalue_problem(store)
+        self.N = len(self.lam)
+        return
+
+    def _initialize_dual(self, store=False):
+        """Complex design x + i h p (the complex-step check of the examples, thermal.py:652-661): the imaginary part is
+        carried as a first-order tangent through the real fp64 kernels -- filter, material law, assembly, LDL^T, Lanczos
+        (eigd_b200/dual.py) -- and ``lam`` / ``Q`` come back as complex host arrays (value + i tangent), which is what
+        the reference's complex run returns.  As in the reference, only ``BasicLanczos`` supports it."""
+        if self.solver_type == "IRAM":
+            raise NotImplementedError("complex-step designs need solver_type='BasicLanczos' (as in the reference: ARPACK is real)")
+        x = np.asarray(self.x)
+        xr, xt = np.ascontiguousarray(x.real), np.ascontiguousarray(x.imag)
+        self.x_d = to_dev(xr)
+        self.rho = self.fltr.apply(self.x_d)
+        rho_t = self.fltr.apply_tangent(self.x_d, to_dev(xt))
+        self.rhoE = self.prob.set_density(rho=self.rho)
+        K, M = self.prob.assemble()
+        Kt, Mt = self.prob.assemble_tangent(rho_t)
+        coords, dofpn = self.prob.dof_coords()
+        if self.symbolic is None:
+            sym = D.Symbolic(self.prob.indptr, self.prob.indices, self.nvars, coords=coords, dof_per_node=dofpn)
+            self.symbolic = (sym, sym.assembly_map_device(K.indptr, K.indices))
+        shifted = K.with_values(D.axpby(1.0, K.data, -float(self.sigma), M.data))
+        self.factor = SpLuOperator(shifted, symbolic=self.symbolic)
+        self.factor.tangent = K.with_values(D.axpby(1.0, Kt.data, -float(self.sigma), Mt.data))
+        self.factor.dtype = np.dtype(np.complex128)
+        self.K, self.M = K, M
+        ncomp = self.N + self.nrigid
+        if self.m is None:
+            self.m = max(3 * ncomp + 1, 60)
+        self.eig_solver = BasicLanczos(N=ncomp, m=self.m, eig_atol=self.eig_atol, tol=self.tol, Ntarget=self.Ntarget)
+        lam, Phi = self.eig_solver.solve((K, Kt), (M, Mt), self.factor, self.sigma)
+        self.lam0, self.Q0 = np.asarray(lam), np.asarray(Phi)               # complex host arrays
+        self.lam, self.Q = self.lam0[self.nrigid:], self.Q0[:, self.nrigid:]
         self.N = len(self.lam)
         return
 
@@ -161,6 +197,9 @@ class ThermalTopologyAnalysis(_Q4Analysis):
 
     def get_thermal_compliance(self, vec):
         """sum_{i>=1} (phi_i . vec)^2 / lam_i   (thermal.py:428-434)"""
+        if not is_dev(self.Q):                      # dual-number mode: complex host eigenpairs, N-sized host algebra
+            c = np.asarray(self.Q).T @ (to_host(vec) if is_dev(vec) else np.asarray(vec))
+            return np.sum(c[1:] ** 2 / self.lam[1:])
         c = to_host(D.gemm_tn(self.Q, to_dev(vec))).ravel()
         return float(np.sum(c[1:] ** 2 / self.lam[1:]))
 

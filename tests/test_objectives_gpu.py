@@ -76,3 +76,47 @@ def test_helmholtz_filter_vs_reference(g):
     assert rel(f0.apply_gradient(np.array(g["hf_g"]), np.array(g["hf0_x"])), g["hf0_grad"]) < 1e-10
     with pytest.raises(ValueError):
         fe.NodeFilter(g["hf_conn"], g["hf_X"], r0=0.1, ftype="nope")
+
+
+def test_complex_step_design_through_the_device_driver():
+    """examples/thermal.py:652-661: the design is perturbed by i h p and the eigenpairs' imaginary parts are read as
+    directional derivatives.  The device driver carries the tangent through filter, material law, assembly, LDL^T and the
+    Lanczos recurrence as dual numbers (exact to first order, any h); compared with the reference's own complex run
+    (h = 1e-30) frozen in tests/golden/thermal_basiclanczos.npz."""
+    from conftest import load_golden
+    from eigd_b200 import device as D, topo as T
+    D.init()
+    g = load_golden("thermal_basiclanczos")
+    model = T.make_thermal_model(nx=int(g["nx"]), ny=int(g["ny"]), Lx=1.0, Ly=0.8, N=int(g["N"]), m=int(g["m_max"]),
+                                 solver_type="BasicLanczos", tol=1e-14, adjoint_method="sibk", rtol=1e-12)
+    h = 1e-6
+    model.x = np.array(g["x"]).astype(complex)
+    model.x.imag += h * g["cs_pert"]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model.initialize()
+    lam, Q = np.asarray(model.lam), np.asarray(model.Q)
+    assert np.iscomplexobj(lam) and np.iscomplexobj(Q)
+    scale = np.abs(g["cs_lam"]).max()
+    assert np.abs(lam.real - g["cs_lam"]).max() < 1e-10 * scale
+    assert np.abs(lam.imag / h - g["cs_lam_tan"]).max() < 1e-8 * np.abs(g["cs_lam_tan"]).max()
+    sgn = np.sign(np.einsum("ij,ij->j", Q.real, g["cs_Phi"]))
+    assert rel(Q.real * sgn, g["cs_Phi"]) < 1e-8
+    assert rel(Q.imag / h * sgn, g["cs_Phi_tan"]) < 1e-6
+    # the objective of the example in complex arithmetic: its imaginary part is the directional derivative
+    vec = np.random.default_rng(2).uniform(size=model.nnodes)
+    c = model.get_thermal_compliance(vec)
+    model.x = np.array(g["x"]).real.copy()
+    model.adjoint_options = {"lanczos_guess": True}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model.initialize()
+        model.initialize_adjoint()
+        model.add_thermal_compliance_derivative(1.0, vec)
+        model.finalize_adjoint()
+    ans = float(g["cs_pert"] @ model.xb.cpu().numpy())
+    assert abs(c.imag / h - ans) <= 1e-7 * abs(ans), (c.imag / h, ans)
+    with pytest.raises(NotImplementedError):
+        m2 = T.make_thermal_model(nx=8, ny=8, N=3, solver_type="IRAM")
+        m2.x = m2.x.astype(complex)
+        m2.initialize()
