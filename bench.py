@@ -487,6 +487,7 @@ def run_ours(args, rank, world):
         A_h.data = vals
     prob = model.prob
     Phib_h = D.pinned_empty((model.nnodes, N))
+    Phib_t, vec_t = torch.from_numpy(Phib_h), torch.from_numpy(vec_h)
 
     def step_e2e():
         f = E.SpLuOperator(mat_h, coords=model.X, dof_per_node=1)
@@ -494,10 +495,16 @@ def run_ours(args, rank, world):
         s.seed = 0
         s.sharding = shard
         lam, Phi = s.solve(K_h, M_h, f, SIGMA)
-        c = Phi.T @ vec_h                                   # objective seeds on the host, as the example does
-        Phib = np.multiply.outer(vec_h, 2.0 * c / lam, out=Phib_h)     # written into page-locked memory
+        # objective seeds on the host, as the example does (thermal.py:436-442: c_i = phi_i . vec, Qb_i = 2 c_i vec / lam_i,
+        # lamb_i = -c_i^2 / lam_i^2), written straight into page-locked memory.  Vectorised host code: numpy's broadcast
+        # product with an inner dimension of 10 takes 10 ms here, torch's CPU outer product 0.3 ms.
+        c = vec_h @ Phi
+        coef = 2.0 * c / lam
+        coef[0] = 0.0
+        torch.outer(vec_t, torch.from_numpy(coef), out=Phib_t)
+        Phib = Phib_h
         lamb = -(c * c) / lam**2
-        Phib[:, 0], lamb[0] = 0.0, 0.0
+        lamb[0] = 0.0
         psi, data = s.solve_adjoint(Phib, method="sibk", rtol=RTOL, lanczos_guess=True)
         dfdx = np.zeros(prob.nelems)
         s.add_total_derivative(lamb, Phib, psi, prob.dAdx, prob.dBdx, dfdx, adj_corr_data=data, deriv_type="tensor")
