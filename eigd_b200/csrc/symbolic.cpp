@@ -4,7 +4,7 @@
 // amalgamation + width cap), front row structures, child->parent relative indices, levels.
 //
 // The reference has no counterpart (SuperLU/COLAMD inside scipy splu,
-// eigd/eigenvector_derivatives.py:13); results are pinned against oracle/symbolic_oracle.py.
+// eigd/eigenvector_derivatives.py:13); results are pinned against oracle/multifrontal_oracle.py (tests/test_symbolic_cpu.py).
 #include "symbolic.hpp"
 #include "../../include/eigd_b200.h"
 
