@@ -33,6 +33,12 @@ import sys
 import time
 import warnings
 
+# Host threading of BOTH arms.  The worker threads of an OpenMP runtime (torch's CPU operators here) spin for a while
+# after every parallel region by default; on the GPU box those spinning workers starve the thread that drives the
+# GPU (stream synchronisations, pageable staging copies): the numpy-API gradient took 76-87 ms instead of 33-34 ms
+# (profiles/r2_e2e_host_threads.txt).  Passive waiting has to be chosen before the runtime is loaded.
+os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -511,6 +517,9 @@ def run_ours(args, rank, world):
         return dfdx
 
     e2e_s, h2d, d2h = None, 0, 0
+    # the caller's host code (objective seeds: one 20 MB outer product per step) on 4 threads: waking 16 workers for it
+    # costs more than it saves (seeds 2.6 ms with 16 threads, 1.7 ms with 4; profiles/r2_e2e_host_threads.txt)
+    torch.set_num_threads(max(1, min(4, os.cpu_count() or 1)))
     if not args.no_e2e:
         for _ in range(2):
             step_e2e()

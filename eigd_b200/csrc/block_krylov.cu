@@ -11,8 +11,9 @@
 // One call runs the block steps of a restart cycle without returning to the host.  Per step (m = basis vectors so far,
 // j = first vector of the block being expanded):
 //     W   = factor^{-1} BV[j : j+P]                      (one P-column solve, + refinement steps)
-//     H1  = BV[0:m] W,  W -= V[0:m]^T H1                 (classical Gram-Schmidt in the B inner product)
-//     H2  = BV[0:m] W,  W -= V[0:m]^T H2                 (unconditional second pass, DGKS)
+//     H1  = BV[lo:m] W, W -= V[lo:m]^T H1                (local Gram-Schmidt pass in the B inner product: lo = j - P, the two
+//                                                         blocks of the three-term recurrence; lo = 0 after a restart)
+//     H2  = BV[0:m] W,  W -= V[0:m]^T H2                 (unconditional full pass: full reorthogonalisation)
 //     BW  = B W,  G = W^T BW = R1^T R1,  W <- W R1^-1, BW <- BW R1^-1      (Cholesky QR ...
 //     G2  = W^T BW = R2^T R2,  W <- W R2^-1, BW <- BW R2^-1                 ... twice: orthonormal to rounding)
 //     V[m : m+P] = W, BV[m : m+P] = BW;  A_j = (H1 + H2)[j : j+P] (diagonal block), R_j = R2 R1 (sub-diagonal block)
@@ -21,6 +22,8 @@
 // Storage as in krylov.cu: V and BV are (ncv + P) x n row-major (one vector per row, leading dimension ld).
 #include "common.cuh"
 #include "../../include/eigd_b200.h"
+
+#include <cstdlib>
 
 namespace {
 
@@ -318,6 +321,8 @@ int extend(eigd_factor* f, int refine, int n, const int* mp, const int* mi, cons
            double* H1, double* H2, double* scratch, double* work, double* work2) {
   int rc;
   int step = 0;
+  static int local_first = -1;          // EIGD_LANCZOS_LOCAL=0: two full passes (developer comparison runs)
+  if (local_first < 0) { const char* e = getenv("EIGD_LANCZOS_LOCAL"); local_first = e ? atoi(e) : 1; }
   for (int j = j0, m = m0; j < ncv; j += P, m += P, ++step) {
     const double* bvj = BV + (int64_t)j * ld;
     double* W = V + (int64_t)m * ld;
@@ -334,11 +339,17 @@ int extend(eigd_factor* f, int refine, int n, const int* mp, const int* mi, cons
       EIGD_LAUNCH(block_add_to_kernel, ew_grid((int64_t)n * P), 256, 0, (int64_t)n, P, dx, (int64_t)n, W, ld);
       EIGD_CHECK_LAUNCH();
     }
-    // classical Gram-Schmidt against V[0:m] in the B inner product, twice
-    if ((rc = dots<P>(n, m, BV, ld, W, ld, H1, work))) return rc;
-    if ((rc = axpy<P>(n, m, V, ld, H1, -1.0, W, ld))) return rc;
+    // Gram-Schmidt in the B inner product: a LOCAL pass against the vectors W is coupled to in exact arithmetic -- the
+    // block being expanded and its predecessor (block three-term recurrence), or the whole basis in the first step
+    // after a thick restart (the locked Ritz vectors: the arrow) -- then one FULL classical pass against V[0:m].  The
+    // local pass takes out the large components (where the cancellation is), the full pass the O(eps)-relative ones
+    // left along the older vectors: full reorthogonalisation at half the basis traffic of two full passes.
+    const int lo = (step == 0 || local_first == 0) ? 0 : (j - P > 0 ? j - P : 0);
+    if ((rc = dots<P>(n, m - lo, BV + (int64_t)lo * ld, ld, W, ld, H1, work))) return rc;
+    if ((rc = axpy<P>(n, m - lo, V + (int64_t)lo * ld, ld, H1, -1.0, W, ld))) return rc;
     if ((rc = dots<P>(n, m, BV, ld, W, ld, H2, work))) return rc;
-    if ((rc = axpy<P>(n, m, V, ld, H2, -1.0, W, ld, H1, Ablk + (int64_t)step * P * P, j))) return rc;
+    // diagonal block A_j = (H1 + H2)[j : j + P]; H1 holds rows lo .. m-1
+    if ((rc = axpy<P>(n, m, V, ld, H2, -1.0, W, ld, H1 - (int64_t)lo * P, Ablk + (int64_t)step * P * P, j))) return rc;
     // BW = B W, then orthonormalise the block
     if ((rc = eigd_csr_spmm(n, bp, bi, bv, W, 1, ld, BW, 1, ld, P, 1.0, 0.0))) return rc;
     if ((rc = cholqr2<P>(n, W, BW, ld, Rblk + (int64_t)step * P * P, scratch, work))) return rc;

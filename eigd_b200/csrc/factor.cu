@@ -575,6 +575,7 @@ panel_build_kernel(SymDev d, const int2* __restrict__ tasks, const double* __res
   const double* X = xinv + d.xoff[s];
   double* S = sfwd + d.soff[s];
   double* St = sbwd + d.soff[s];
+  const int thf = d.th_f[s], thb = d.th_b[s];   // tile-major storage above the cut of the solve plan (0: column-major)
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const bool below = r0 + NB > nc;          // the tile holds rows of L21
   for (int jb = 0; jb * NB < nc; ++jb) {
@@ -591,7 +592,12 @@ panel_build_kernel(SymDev d, const int2* __restrict__ tasks, const double* __res
       double v = 0.0;
       if (r < f && c < nc) {
         v = (r < nc) ? X[r + (int64_t)c * nc] : -acc[qq];
-        S[r + (int64_t)c * f] = v;
+        if (thf) {
+          const int t0 = r / thf * thf;                        // first row of the row tile; th rows in it
+          S[(int64_t)t0 * nc + (int64_t)c * min(thf, (int)f - t0) + (r - t0)] = v;
+        } else {
+          S[r + (int64_t)c * f] = v;
+        }
       }
       Ts[tx][ty + 8 * qq] = v;
     }
@@ -599,7 +605,14 @@ panel_build_kernel(SymDev d, const int2* __restrict__ tasks, const double* __res
 #pragma unroll
     for (int qq = 0; qq < 4; ++qq) {
       int rr = r0 + ty + 8 * qq, c = c0 + tx;
-      if (rr < f && c < nc) St[c + (int64_t)rr * nc] = Ts[ty + 8 * qq][tx];
+      if (rr < f && c < nc) {
+        if (thb) {
+          const int t0 = c / thb * thb;                        // first pivot column of the column tile; tw columns in it
+          St[(int64_t)t0 * f + (int64_t)rr * min(thb, nc - t0) + (c - t0)] = Ts[ty + 8 * qq][tx];
+        } else {
+          St[c + (int64_t)rr * nc] = Ts[ty + 8 * qq][tx];
+        }
+      }
     }
     __syncthreads();
   }
@@ -638,8 +651,8 @@ static void factor_layout(const eigd_symbolic* s, const SymDevHolder* h, int max
   sz[1] = align256(h->linv_total * 8);                 // linv
   sz[2] = align256(h->xinv_total * 8);                 // xinv
   sz[3] = align256(h->xinv_total * 8);                 // xtmp
-  sz[4] = align256(h->panel_total * 8);                // sfwd
-  sz[5] = align256(h->panel_total * 8);                // sbwd
+  sz[4] = align256(h->panel_total * 8 + 16);           // sfwd (+ one 16-byte unit: bulk copies round a slice up to 16 bytes)
+  sz[5] = align256(h->panel_total * 8 + 16);           // sbwd
   sz[6] = align256((int64_t)s->n * 8);                 // dval
   sz[7] = align256((int64_t)s->n * 8);                 // dinv
   sz[8] = align256(3 * sumf * kc * 8);                 // wbuf: three child slabs, one plane per right-hand side

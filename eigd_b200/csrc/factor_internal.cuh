@@ -26,6 +26,7 @@ struct SymDev {
   int64_t* xoff;      // full-inverse offsets (prefix of nc * nc)
   int* sn_parent;
   int *child_ptr, *child_idx;
+  int *th_f, *th_b;   // per supernode: tile height of the tile-major S / S^T solve panel (solve_plan.hpp), 0 = column-major
 };
 
 struct Launch {
@@ -68,8 +69,9 @@ struct eigd_factor {
   double* linv = nullptr;     // inverses of the 32x32 unit-lower diagonal blocks
   double* xinv = nullptr;     // full inverse of every L11 (nc x nc, column-major)
   double* xtmp = nullptr;     // scratch of the same size (recursive-doubling products)
-  double* sfwd = nullptr;     // solve panels S = [L11^-1 ; -L21 L11^-1], f x nc column-major
-  double* sbwd = nullptr;     // S^T, nc x f column-major
+  double* sfwd = nullptr;     // solve panels S = [L11^-1 ; -L21 L11^-1], f x nc: column-major below the cut of the solve
+                              // plan, tile-major above it (solve_plan.hpp)
+  double* sbwd = nullptr;     // S^T, nc x f, likewise
   double* dval = nullptr;
   double* dinv = nullptr;
   double* wbuf = nullptr;     // forward-sweep update vectors: 3 slabs x kmax planes x (sum of front sizes)

@@ -68,13 +68,18 @@ struct SolveArgs {
   unsigned long long bar_base;
   unsigned* cnt;                  // completion counters: 2 * supernode + direction, monotone over the solves of a factor
   unsigned epoch;                 // number of this solve (1, 2, ...): counter c is complete at epoch * tiles(c)
-  int dbg;                        // developer ablation (EIGD_SOLVE_DBG): bit 0 no operand loads, bit 1 no panel copies, bit 2 no stores
+  int dbg;                        // developer ablation (EIGD_SOLVE_DBG): bit 0 no operand loads, bit 1 no panel copies, bit 2 no
+                                  // stores (subtree kernels); bit 3: the panel pipeline copies nothing, every tile of the
+                                  // level kernel reads its slice from global memory (the path of a slice larger than the ring)
   int p_begin, p_end;             // phases run by the cooperative kernel
   int ring_w;                     // bytes of shared-memory panel buffer per warp (front mode of the subtree phases)
+  int lring_w;                    // bytes of shared-memory panel ring per warp in the level kernel (0: no panel pipeline)
   int rec_cap;                    // tile records of a slot that fit in shared memory
   unsigned long long* times;      // developer profiling: %globaltimer of CTA 0 after every phase (NULL: off)
   long long* trace;               // developer profiling: clock64 of CTA 0 / warp 0 inside its first tile of every level
-                                  // phase, 8 slots per phase: start, waited, product done, reduced, stored, signalled
+                                  // phase, 16 slots per phase: 0 start, 1 waited, 2 product done, 3 reduced, 4 stored,
+                                  // 5 signalled, 6 slot (record + panel slice) there, 7 end of tile, 8 top of the phase loop,
+                                  // 9 dispatch
 };
 
 // vectors produced earlier in the same launch by other SMs are read through L2 (ld.global.cg): L1 is
@@ -231,8 +236,8 @@ __device__ __forceinline__ void warp_panel_product(const double* __restrict__ M,
 
 // Grid-wide barrier, only for the rare in-kernel phases that are not synchronised by completion counters (a subtree
 // phase executed inside the cooperative kernel, the in-kernel copy of the permuted right-hand side).
-__device__ __forceinline__ void grid_barrier(unsigned long long* ctr, unsigned long long target) {
-  __syncthreads();
+// (the caller puts a CTA barrier -- of all its participating warps -- on both sides)
+__device__ __forceinline__ void grid_barrier_arrive_wait(unsigned long long* ctr, unsigned long long target) {
   if (threadIdx.x == 0) {
     unsigned long long v;
     asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(ctr) : "memory");
@@ -240,7 +245,6 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* ctr, unsigned l
       asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(ctr) : "memory");
     } while (v < target);
   }
-  __syncthreads();
 }
 __host__ __device__ inline bool barrier_between(const PhaseRec& a, const PhaseRec& b, int p) {
   return a.ws == 0 || b.ws == 0 || p == 0;
@@ -249,7 +253,8 @@ __host__ __device__ inline bool barrier_between(const PhaseRec& a, const PhaseRe
 // the products of one warp tile: slice `slice` of `ws` of the reduction dimension.
 // use_perm: the right-hand side is gathered from B through perm (first phase; later phases read the
 // permuted copy written during the first one)
-template <int KT, int MC = DefaultMC<KT>::value, int TH = SOLVE_TILE, class WaitFn>
+// TILED: the front's panels are stored tile-major with tile height TH (fronts above the cut, solve_plan.hpp)
+template <int KT, int MC = DefaultMC<KT>::value, int TH = SOLVE_TILE, bool TILED = false, class WaitFn>
 __device__ __forceinline__ void tile_compute(const SolveArgs& a, int dir, bool use_perm, const TileRec& tr, int lane,
                                              int slice, int ws, double* stage, double* acc, WaitFn& wait) {
   constexpr int to = TH;
@@ -261,10 +266,11 @@ __device__ __forceinline__ void tile_compute(const SolveArgs& a, int dir, bool u
   if (dir == 0) {
     // ---- forward: outputs are front rows; acc = S[row, 0:cend) w1 (+ the children's updates of the row)
     const int cend = min(nc, o0 + to);                  // S is lower triangular inside the pivot rows
-    const int per = (cend + ws - 1) / ws;
-    const int c0 = slice * per, c1 = min(cend, c0 + per);
-    const double* M = a.sfwd + tr.soff + min(out, f - 1);
-    warp_panel_product<KT, MCT, TH>(M, f, c0, c1, lane, stage, acc, [&](int c, double* v) {
+    const int per = solve_slice_len(cend, ws);
+    const int c0 = min(cend, slice * per), c1 = min(cend, c0 + per);
+    const int th = min(to, f - o0);                     // rows of this row tile
+    const double* M = TILED ? a.sfwd + tr.soff + (int64_t)o0 * nc + min(lane % to, th - 1) : a.sfwd + tr.soff + min(out, f - 1);
+    warp_panel_product<KT, MCT, TH>(M, TILED ? th : f, c0, c1, lane, stage, acc, [&](int c, double* v) {
       if (use_perm) {
         const int64_t po = __ldg(&a.perm[tr.first + c]);
         const double* bp = a.B + po * a.brs;
@@ -294,10 +300,11 @@ __device__ __forceinline__ void tile_compute(const SolveArgs& a, int dir, bool u
   } else {
     // ---- backward: outputs are pivot columns; acc = S^T[col, o0:f) [z1 ; x2]
     const int len = f - o0;
-    const int per = (len + ws - 1) / ws;
-    const int i0 = o0 + slice * per, i1 = min(f, i0 + per);
-    const double* M = a.sbwd + tr.soff + min(out, nc - 1);
-    warp_panel_product<KT, MCT, TH>(M, nc, i0, i1, lane, stage, acc, [&](int i, double* v) {
+    const int per = solve_slice_len(len, ws);
+    const int i0 = min(f, o0 + slice * per), i1 = min(f, i0 + per);
+    const int tw = min(to, nc - o0);                    // pivot columns of this column tile
+    const double* M = TILED ? a.sbwd + tr.soff + (int64_t)o0 * f + min(lane % to, tw - 1) : a.sbwd + tr.soff + min(out, nc - 1);
+    warp_panel_product<KT, MCT, TH>(M, TILED ? tw : nc, i0, i1, lane, stage, acc, [&](int i, double* v) {
       if (i < nc) add_row<KT>(a.ybuf, tr.first + i, k, v);
       else add_row<KT>(a.xperm, __ldg(&a.sn_rows[tr.row_off + i - nc]), k, v);
     }, wait);
@@ -825,7 +832,7 @@ __global__ void __launch_bounds__(NW * 32, 1) subtree_kernel(SolveArgs a, int p)
 // One level phase: the tiles (height TH) of one level of the tree in one direction, CTA-strided; ws warps share a tile
 // and split its reduction dimension.  A tile waits for the completion counters of the fronts it reads from and
 // increments its own front's counter when its outputs are stored (no grid barrier).
-template <int KT, int TH>
+template <int KT, int TH, bool TILED>
 __device__ __forceinline__ void level_phase(const SolveArgs& a, const PhaseRec& ph, int p, bool use_perm, int lane, int warp,
                                             double* stage, double* part, bool have_next, int4 (*s_next)[5]) {
   const int64_t tile_off = ph.tile_off;
@@ -868,13 +875,13 @@ __device__ __forceinline__ void level_phase(const SolveArgs& a, const PhaseRec& 
       dw.pending = dw.td.ndep > 0;
       if (KT <= 2 && slice == 0) sto = tile_store_request<TH>(a, dir, tr, lane);      // (costs registers: single / pair solves only)
       const bool tr_on = a.trace && blockIdx.x == 0 && ct == 0 && threadIdx.x == 0;
-      if (tr_on) a.trace[8 * p + 0] = clock64();
+      if (tr_on) a.trace[16 * p + 0] = clock64();
       if (a.trace) {              // trace build of the chain: wait first so that the segments separate
         dw(lane);
-        if (tr_on) a.trace[8 * p + 1] = clock64();
+        if (tr_on) a.trace[16 * p + 1] = clock64();
       }
-      tile_compute<KT, DefaultMC<KT>::value, TH>(a, dir, use_perm, tr, lane, slice, ws, stage, acc, dw);
-      if (tr_on) a.trace[8 * p + 2] = clock64();
+      tile_compute<KT, DefaultMC<KT>::value, TH, TILED>(a, dir, use_perm, tr, lane, slice, ws, stage, acc, dw);
+      if (tr_on) a.trace[16 * p + 2] = clock64();
     }
     if (ws > 1) {
       // partial sums of the ws slices meet in shared memory; the slice-0 warp adds them in a FIXED order (bitwise
@@ -902,15 +909,350 @@ __device__ __forceinline__ void level_phase(const SolveArgs& a, const PhaseRec& 
       }
     }
     const bool tr_on2 = a.trace && blockIdx.x == 0 && ct == 0 && threadIdx.x == 0;
-    if (tr_on2) a.trace[8 * p + 3] = clock64();
+    if (tr_on2) a.trace[16 * p + 3] = clock64();
     if (have && slice == 0) {
       if (KT <= 2) tile_store_with<KT, TH>(a, dir, tr, lane, acc, sto);
       else tile_store<KT, TH>(a, dir, tr, lane, acc);
-      if (tr_on2) a.trace[8 * p + 4] = clock64();
+      if (tr_on2) a.trace[16 * p + 4] = clock64();
       signal_done(a.cnt + dw.td.self);
-      if (tr_on2) a.trace[8 * p + 5] = clock64();
+      if (tr_on2) a.trace[16 * p + 5] = clock64();
     }
     if (ws > 1) __syncthreads();
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// ASYNCHRONOUS PANEL PIPELINE of the level phases: a warp-specialised producer / consumer kernel.
+//
+// Measured on the form in which every tile read its panel entries itself (profiles/r2_solve_pipeline.txt): a hop of
+// the dependency chain took ~10 000 cycles, of which only ~2 000 are the hand-off through L2 -- the rest was a burst of
+// 8-byte-per-lane panel loads through the SM's load path, requested only once the CTA had finished its tile of the
+// previous phase, plus several thousand cycles of scalar bookkeeping (tile records, index arithmetic) executed by the
+// same warp between two tiles.  Neither depends on computed data: the schedule is static (phase by phase, CTA-strided,
+// warp = tile / slice) and the panels are constant during a solve.  So the level kernel has a 17th warp, the PRODUCER:
+// lane w of it walks the tile sequence of consumer warp w ahead of time, fetches each tile's record and dependencies,
+// works out the slice of the panel the warp will multiply -- ONE contiguous run in the tile-major panel storage
+// (solve_plan.hpp) -- and requests it into the warp's shared-memory ring with one bulk copy (cp.async.bulk, completion
+// on the slot's "full" mbarrier), up to PIPE_DEPTH tiles ahead, across phase boundaries.  A consumer warp waits for
+// the slot (record + slice already there), for its dependencies' completion counters, gathers its operands, runs the
+// FMAs out of shared memory, hands the slot back through its "empty" mbarrier and stores / signals.  Nothing but the
+// hand-off, the operand gather and the arithmetic is left on the chain.
+constexpr int PIPE_DEPTH = 3;      // slots (record + panel slice) per consumer warp
+constexpr int PIPE_REC_INT4 = 6;   // TileRec (3 x 16 bytes) + TileDep (2 x 16 bytes) + slice descriptor (16 bytes)
+constexpr int PIPE_THREADS = (SOLVE_WARPS + 1) * 32;
+
+struct PipeSmem {              // per consumer warp
+  char* ring;                  // lring_w bytes
+  unsigned long long* full;    // PIPE_DEPTH mbarriers: record written and slice landed
+  unsigned long long* empty;   // PIPE_DEPTH mbarriers: the consumer is done with the slot
+  int4* rec;                   // PIPE_DEPTH x PIPE_REC_INT4
+};
+__device__ __forceinline__ PipeSmem pipe_smem(char* base, int lring_w, int w) {
+  PipeSmem sm;
+  sm.ring = base + (size_t)w * lring_w;
+  char* q = base + (size_t)SOLVE_WARPS * lring_w;
+  sm.full = reinterpret_cast<unsigned long long*>(q) + 2 * PIPE_DEPTH * w;
+  sm.empty = sm.full + PIPE_DEPTH;
+  q += SOLVE_WARPS * 2 * PIPE_DEPTH * 8;
+  sm.rec = reinterpret_cast<int4*>(q) + PIPE_DEPTH * PIPE_REC_INT4 * w;
+  return sm;
+}
+constexpr size_t pipe_smem_misc() { return (size_t)SOLVE_WARPS * (2 * PIPE_DEPTH * 8 + PIPE_DEPTH * PIPE_REC_INT4 * 16); }
+
+__device__ __forceinline__ void consumer_sync() {      // CTA barrier of the 16 consumer warps (the producer is not part of it)
+  asm volatile("bar.sync 1, %0;" ::"n"(SOLVE_WARPS * 32) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok)
+               : "r"(smem_u32(bar)), "r"(parity)
+               : "memory");
+  return ok != 0;
+}
+
+// the part of tile (tr, height th_) that warp `slice` of `ws` multiplies: first reduction index, count, leading dimension
+// (rows of a forward row tile / pivot columns of a backward column tile) and the offset of the run in sfwd / sbwd
+struct SliceDesc {
+  int64_t off;
+  int r0, len, ld;
+};
+__device__ __forceinline__ SliceDesc slice_of(const TileRec& tr, int dir, int th_, int slice, int ws) {
+  const int nc = tr.nc, f = tr.nc + tr.nb, o0 = tr.tile * th_;
+  SliceDesc s;
+  if (dir == 0) {
+    const int cend = min(nc, o0 + th_);
+    const int per = solve_slice_len(cend, ws);
+    s.r0 = min(cend, slice * per);
+    s.len = min(cend, s.r0 + per) - s.r0;
+    s.ld = min(th_, f - o0);
+    s.off = tr.soff + (int64_t)o0 * nc + (int64_t)s.r0 * s.ld;
+  } else {
+    const int per = solve_slice_len(f - o0, ws);
+    s.r0 = min(f, o0 + slice * per);
+    s.len = min(f, s.r0 + per) - s.r0;
+    s.ld = min(th_, nc - o0);
+    s.off = tr.soff + (int64_t)o0 * f + (int64_t)s.r0 * s.ld;
+  }
+  return s;
+}
+
+// tile of consumer warp w in (phase ph, CTA-tile index ct), or -1
+__device__ __forceinline__ int pipe_tile_of(const PhaseRec& ph, int ct, int w) {
+  if (ph.ws <= 0) return -1;
+  const int tpc = SOLVE_WARPS / ph.ws;
+  const int te = ct * tpc + w / ph.ws;
+  return te < ph.ntiles ? te : -1;
+}
+
+// The producer warp.  Lane w < SOLVE_WARPS serves consumer warp w; all lanes run the same non-blocking loop (a lane
+// that cannot advance -- all its slots in use, or no room in the ring yet -- simply tries again), so lanes never wait
+// for each other's consumers.
+template <class PhaseFn>
+__device__ __forceinline__ void pipe_producer(const SolveArgs& a, char* pipe_base, int lane, PhaseFn phase) {
+  const int w = lane;
+  const bool active = w < SOLVE_WARPS;
+  const PipeSmem sm = pipe_smem(pipe_base, a.lring_w, active ? w : 0);
+  // cursor over this consumer warp's tiles: (phase, CTA-tile index); lp >= p_end: exhausted
+  int lp = a.p_begin, lct = blockIdx.x;
+  auto skip = [&]() {
+    while (lp < a.p_end) {
+      if (pipe_tile_of(phase(lp), lct, w) >= 0) return;   // (te grows with ct: no later ct of this phase has a tile either)
+      ++lp;
+      lct = blockIdx.x;
+    }
+  };
+  if (!active) lp = a.p_end;
+  skip();
+  int islot = 0, rslot = 0;            // slot of the next tile to produce / of the oldest tile not known to be released
+  unsigned ipar = 0, rpar = 0;         // phase parity of those slots' barriers
+  int live = 0;                        // tiles produced and not known to be released
+  int last_end = 0;                    // end of the newest ring allocation
+  int qoff[PIPE_DEPTH], qlen[PIPE_DEPTH];
+#pragma unroll
+  for (int d = 0; d < PIPE_DEPTH; ++d) { qoff[d] = -1; qlen[d] = 0; }
+  bool loaded = false;
+  int4 r0 = make_int4(0, 0, 0, 0), r1 = r0, r2 = r0, r3 = r0, r4 = r0;
+  SliceDesc sd;
+  sd.off = 0; sd.r0 = sd.len = sd.ld = 0;
+  int bytes = 0, dir = 0;
+  while (__any_sync(0xffffffffu, lp < a.p_end)) {
+    // one release per round is enough: the consumers take thousands of cycles per tile
+    if (live > 0 && mbar_test(&sm.empty[rslot], rpar)) {
+#pragma unroll
+      for (int d = 0; d < PIPE_DEPTH; ++d)
+        if (d == rslot) qoff[d] = -1;
+      --live;
+      if (++rslot == PIPE_DEPTH) { rslot = 0; rpar ^= 1u; }
+    }
+    if (lp < a.p_end && live < PIPE_DEPTH) {
+      if (!loaded) {
+        const PhaseRec ph = phase(lp);
+        const int te = pipe_tile_of(ph, lct, w);
+        const int4* tp = reinterpret_cast<const int4*>(a.tiles + ph.tile_off + te);
+        const int4* dp = reinterpret_cast<const int4*>(a.deps + ph.tile_off + te);
+        r0 = __ldg(tp); r1 = __ldg(tp + 1); r2 = __ldg(tp + 2);
+        r3 = __ldg(dp); r4 = __ldg(dp + 1);
+        dir = ph.dir;
+        sd = slice_of(unpack_tile(r0, r1, r2), dir, (int)(ph.pad & 0xff), w % ph.ws, ph.ws);
+        bytes = (sd.len * sd.ld * 8 + 15) & ~15;
+        loaded = true;
+      }
+      int off;
+      bool clash = false;
+      if (bytes == 0) off = -2;                                 // empty slice: nothing to copy
+      else if (bytes > a.lring_w || (a.dbg & 8)) off = -1;      // larger than the ring: the tile reads it from global memory
+      else {
+        off = (last_end + 127) & ~127;
+        if (off + bytes > a.lring_w) off = 0;
+#pragma unroll
+        for (int d = 0; d < PIPE_DEPTH; ++d)
+          if (qoff[d] >= 0 && off < qoff[d] + qlen[d] && qoff[d] < off + bytes) clash = true;
+      }
+      if (!clash) {
+        int4* rec = sm.rec + islot * PIPE_REC_INT4;
+        rec[0] = r0; rec[1] = r1; rec[2] = r2; rec[3] = r3; rec[4] = r4;
+        rec[5] = make_int4(sd.r0, sd.len, sd.ld, off);
+        if (off >= 0) {
+          bulk_load(sm.ring + off, (dir == 0 ? a.sfwd : a.sbwd) + sd.off, (unsigned)bytes, &sm.full[islot]);
+          last_end = off + bytes;
+        } else {
+          mbar_arrive(&sm.full[islot]);
+        }
+#pragma unroll
+        for (int d = 0; d < PIPE_DEPTH; ++d)
+          if (d == islot) { qoff[d] = off; qlen[d] = bytes; }
+        ++live;
+        if (++islot == PIPE_DEPTH) { islot = 0; ipar ^= 1u; }
+        loaded = false;
+        lct += gridDim.x;
+        skip();
+      }
+    }
+  }
+  (void)ipar;
+}
+
+// the products of one warp tile with its panel slice in shared memory (sbuf: the slice, leading dimension ld)
+template <int KT, int TH, class WaitFn>
+__device__ __forceinline__ void tile_compute_smem(const SolveArgs& a, int dir, bool use_perm, const TileRec& tr, int lane,
+                                                  int slice, int sr0, int slen, int sld, const double* sbuf, double* stage,
+                                                  double* acc, WaitFn& wait) {
+  constexpr int nks = 32 / TH;
+  const int k = a.k;
+  const int nc = tr.nc, f = tr.nc + tr.nb;
+  const int o0 = tr.tile * TH;
+  const int g = lane / TH;
+  const int out = o0 + (lane % TH);
+  const double* mp = sbuf + min(lane % TH, sld - 1) + g * sld;
+  const int step = nks * sld;
+  for (int cc = 0; cc < slen; cc += 32) {
+    const int ncol = min(32, slen - cc);
+    double v[KT];
+#pragma unroll
+    for (int r = 0; r < KT; ++r) v[r] = 0.0;
+    wait(lane);
+    if (lane < ncol) {
+      const int c = sr0 + cc + lane;
+      if (dir == 0) {
+        if (use_perm) {
+          const int64_t po = __ldg(&a.perm[tr.first + c]);
+          const double* bp = a.B + po * a.brs;
+#pragma unroll
+          for (int r = 0; r < KT; ++r)
+            if (r < k) v[r] = bp[(int64_t)r * a.bcs];
+        } else {
+          add_row<KT>(a.bperm, tr.first + c, k, v);
+        }
+        child_add<KT>(a, tr.w_off + c, tr.link, v);
+      } else {
+        if (c < nc) add_row<KT>(a.ybuf, tr.first + c, k, v);
+        else add_row<KT>(a.xperm, __ldg(&a.sn_rows[tr.row_off + c - nc]), k, v);
+      }
+    }
+    // forward: the children's updates of this output row go straight into the sum (requested together with the operands;
+    // slice 0 always has a first chunk: its range starts at column 0)
+    if (dir == 0 && cc == 0 && slice == 0 && lane < TH && out >= nc && out < f) child_add<KT>(a, tr.w_off + out, tr.link, acc);
+#pragma unroll
+    for (int r = 0; r < KT; ++r) stage[r * 32 + lane] = v[r];
+    __syncwarp();
+    const double* mc = mp + (int64_t)cc * sld;
+    const int nj = (ncol + nks - 1) / nks;
+#pragma unroll 8
+    for (int j = 0; j < nj; ++j) {
+      const int col = g + j * nks;
+      const double m = col < ncol ? mc[j * step] : 0.0;
+#pragma unroll
+      for (int r = 0; r < KT; ++r) acc[r] = fma(m, stage[r * 32 + (col & 31)], acc[r]);
+    }
+    __syncwarp();
+  }
+  wait(lane);
+  if (TH < 32) {
+#pragma unroll
+    for (int o = TH; o < 32; o <<= 1)
+#pragma unroll
+      for (int r = 0; r < KT; ++r) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
+  }
+}
+
+struct ConsumerState {
+  int slot;          // slot of this warp's next tile
+  unsigned par;      // parity of that slot's barriers
+};
+
+// One level phase on the consumer side of the panel pipeline: as level_phase, but the tile's record, dependencies and
+// slice descriptor come from the warp's current slot and the panel slice from its shared-memory ring.
+template <int KT, int TH>
+__device__ __forceinline__ void level_phase_pipe(const SolveArgs& a, const PhaseRec& ph, int p, bool use_perm, int lane, int warp,
+                                                 double* stage, double* part, ConsumerState& cs, const PipeSmem& sm) {
+  const int dir = ph.dir, ws = ph.ws, ntiles = ph.ntiles;
+  const int lws = __ffs(ws) - 1;                            // ws is a power of two <= SOLVE_WARPS (pick_ws): no divisions here
+  const int ltpc = 4 - lws, tpc = 1 << ltpc;
+  static_assert(SOLVE_WARPS == 16, "level_phase_pipe: log2(SOLVE_WARPS) == 4");
+  const int sub = warp >> lws, slice = warp & (ws - 1);
+  const int nct = (ntiles + tpc - 1) >> ltpc;
+  for (int ct = blockIdx.x; ct < nct; ct += gridDim.x) {
+    const int te = (ct << ltpc) + sub;
+    const bool have = te < ntiles;
+    double acc[KT];
+#pragma unroll
+    for (int r = 0; r < KT; ++r) acc[r] = 0.0;
+    TileRec tr;
+    tr.first = tr.nc = tr.nb = tr.tile = 0;
+    tr.soff = tr.w_off = tr.row_off = tr.link = 0;
+    DepWait dw;
+    dw.cnt = a.cnt;
+    dw.ovf = a.dep_ovf;
+    dw.epoch = a.epoch;
+    dw.pending = false;
+    dw.td.self = 0;
+    StoreOps sto;
+    sto.di = 0.0;
+    sto.dst = 0;
+    const bool tr_on = a.trace && blockIdx.x == 0 && ct == (int)blockIdx.x && threadIdx.x == 0;
+    if (have) {
+      if (tr_on) a.trace[16 * p + 0] = clock64();
+      mbar_wait(&sm.full[cs.slot], cs.par);                 // record written, panel slice landed
+      const int4* r = sm.rec + cs.slot * PIPE_REC_INT4;
+      tr = unpack_tile(r[0], r[1], r[2]);
+      const int4 d0 = r[3], d1 = r[4], sl = r[5];
+      dw.td.self = d0.x; dw.td.ndep = d0.y; dw.td.d0 = d0.z; dw.td.n0 = d0.w;
+      dw.td.d1 = d1.x; dw.td.n1 = d1.y; dw.td.ovf = d1.z; dw.td.pad = 0;
+      dw.pending = dw.td.ndep > 0;
+      if (KT <= 2 && slice == 0) sto = tile_store_request<TH>(a, dir, tr, lane);
+      if (a.trace) {                // trace build of the chain: wait first so that the segments separate
+        if (tr_on) a.trace[16 * p + 6] = clock64();
+        dw(lane);
+        if (tr_on) a.trace[16 * p + 1] = clock64();
+      }
+      // the slice: in the warp's ring, or (larger than the ring, rare) where it lies in global memory -- same code,
+      // generic loads
+      const double* sbuf = reinterpret_cast<const double*>(sm.ring + max(sl.w, 0));
+      if (sl.w == -1) sbuf = (dir == 0 ? a.sfwd : a.sbwd) + slice_of(tr, dir, TH, slice, ws).off;
+      tile_compute_smem<KT, TH>(a, dir, use_perm, tr, lane, slice, sl.x, sl.y, sl.z, sbuf, stage, acc, dw);
+      __syncwarp();                 // every lane is done with the slot
+      if (lane == 0) mbar_arrive(&sm.empty[cs.slot]);
+      if (++cs.slot == PIPE_DEPTH) { cs.slot = 0; cs.par ^= 1u; }
+      if (tr_on) a.trace[16 * p + 2] = clock64();
+    }
+    if (ws > 1) {
+#pragma unroll
+      for (int r = 0; r < KT; ++r) part[(warp * KT + r) * 32 + lane] = acc[r];
+      consumer_sync();
+      if (have && slice == 0 && KT > 2) {
+        for (int s = 1; s < ws; ++s)
+#pragma unroll
+          for (int r = 0; r < KT; ++r) acc[r] += part[((warp + s) * KT + r) * 32 + lane];
+      }
+      if (have && slice == 0 && KT <= 2) {
+#pragma unroll
+        for (int r = 0; r < KT; ++r) {
+          double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+          for (int s = 1; s < ws; s += 4) {
+            p0 += part[((warp + s) * KT + r) * 32 + lane];
+            if (s + 1 < ws) p1 += part[((warp + s + 1) * KT + r) * 32 + lane];
+            if (s + 2 < ws) p2 += part[((warp + s + 2) * KT + r) * 32 + lane];
+            if (s + 3 < ws) p3 += part[((warp + s + 3) * KT + r) * 32 + lane];
+          }
+          acc[r] += (p0 + p1) + (p2 + p3);
+        }
+      }
+    }
+    if (tr_on) a.trace[16 * p + 3] = clock64();
+    if (have && slice == 0) {
+      if (KT <= 2) tile_store_with<KT, TH>(a, dir, tr, lane, acc, sto);
+      else tile_store<KT, TH>(a, dir, tr, lane, acc);
+      if (tr_on) a.trace[16 * p + 4] = clock64();
+      signal_done(a.cnt + dw.td.self);
+      if (tr_on) a.trace[16 * p + 5] = clock64();
+    }
+    if (ws > 1) consumer_sync();
+    if (tr_on) a.trace[16 * p + 7] = clock64();
   }
 }
 
@@ -919,14 +1261,25 @@ __device__ __forceinline__ void level_phase(const SolveArgs& a, const PhaseRec& 
 // walks its share in that order, and a tile spins only on the completion counters of the fronts it reads from
 // (TileDep).  A dependency always lies earlier in the global order and all CTAs are co-resident (cooperative
 // launch), so the earliest unfinished tile can always run: no deadlock.
-template <int KT>
-__global__ void __launch_bounds__(SOLVE_WARPS * 32, 1) solve_kernel(SolveArgs a) {
+template <int KT, bool PIPE>
+__global__ void __launch_bounds__(PIPE ? PIPE_THREADS : SOLVE_WARPS * 32, 1) solve_kernel(SolveArgs a) {
   extern __shared__ double smem[];
   __shared__ PhaseRec s_phase[MAX_PHASES_SMEM];
-  __shared__ int4 s_next[SOLVE_WARPS][5];                  // first tile record + dependencies of the next phase, per warp
+  __shared__ int4 s_next[PIPE ? 1 : SOLVE_WARPS][5];       // first tile record + dependencies of the next phase, per warp
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double* stage = smem + warp * (32 * KT);                 // [KT][32] per warp
-  double* part = smem + SOLVE_WARPS * 32 * KT;             // [SOLVE_WARPS][KT][32] partial sums
+  constexpr bool pipe = PIPE;         // tile-major panels + panel pipeline (a.lring_w > 0), or the column-major form
+  constexpr int NT = SOLVE_WARPS * 32;                      // consumer threads (the whole CTA without the pipeline)
+  double* stage = smem + (warp % SOLVE_WARPS) * (32 * KT);  // [KT][32] per warp
+  double* part = smem + SOLVE_WARPS * 32 * KT;              // [SOLVE_WARPS][KT][32] partial sums
+  // panel pipeline: per-warp rings | full / empty mbarriers | slot records, behind the partial sums
+  char* pipe_base = reinterpret_cast<char*>(smem + 2 * SOLVE_WARPS * 32 * KT);
+  PipeSmem sm;
+  sm.ring = nullptr; sm.full = sm.empty = nullptr; sm.rec = nullptr;
+  if constexpr (pipe) {
+    sm = pipe_smem(pipe_base, a.lring_w, warp % SOLVE_WARPS);
+    if (warp < SOLVE_WARPS && lane < 2 * PIPE_DEPTH) mbar_init(&sm.full[lane], 1);   // full[0..D) and empty[0..D) are adjacent
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   unsigned long long target = a.bar_base;
   if (a.times && blockIdx.x == 0 && threadIdx.x == 0 && a.p_begin == 0) {
     unsigned long long t;
@@ -939,8 +1292,23 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32, 1) solve_kernel(SolveArgs a)
     for (int e = threadIdx.x; e < 2 * min(a.nphases, MAX_PHASES_SMEM); e += blockDim.x) dst[e] = __ldg(src + e);
   }
   __syncthreads();
+  auto phase_of = [&](int p) { return p < MAX_PHASES_SMEM ? s_phase[p] : a.phases[p]; };
+  if constexpr (pipe) {
+    if (warp == SOLVE_WARPS) {          // the producer warp: streams records and panel slices, then leaves
+      pipe_producer(a, pipe_base, lane, phase_of);
+      return;
+    }
+  }
+  auto cta_sync = [&]() {
+    if constexpr (pipe) consumer_sync();
+    else __syncthreads();
+  };
+  ConsumerState cs;
+  cs.slot = 0;
+  cs.par = 0u;
   bool have_next = false;                                  // s_next[warp] holds this warp's first tile of phase p
   for (int p = a.p_begin; p < a.p_end; ++p) {
+    if (a.trace && blockIdx.x == 0 && threadIdx.x == 0) a.trace[16 * p + 8] = clock64();
     const PhaseRec ph = p < MAX_PHASES_SMEM ? s_phase[p] : a.phases[p];
     const int64_t tile_off = ph.tile_off;
     const int dir = ph.dir, ws = ph.ws, ntiles = ph.ntiles;
@@ -952,7 +1320,7 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32, 1) solve_kernel(SolveArgs a)
     if (p + 1 < a.p_end) {
       const PhaseRec nx = (p + 1) < MAX_PHASES_SMEM ? s_phase[p + 1] : a.phases[p + 1];
       bar_after = barrier_between(ph, nx, p);
-      if (nx.ws > 0) {
+      if (nx.ws > 0 && !pipe) {
         const int te = (int)blockIdx.x * (SOLVE_WARPS / nx.ws) + warp / nx.ws;
         if (te < nx.ntiles) {
           nxt_have = true;
@@ -964,7 +1332,7 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32, 1) solve_kernel(SolveArgs a)
     if (p == 0 && a.p_end > 1) {
       // permuted copy of the right-hand side for the later phases (coalesced writes, gathered reads)
       const int k = a.k;
-      for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < (int64_t)a.n * k; e += (int64_t)gridDim.x * blockDim.x) {
+      for (int64_t e = (int64_t)blockIdx.x * NT + threadIdx.x; e < (int64_t)a.n * k; e += (int64_t)gridDim.x * NT) {
         const int64_t i = e / k;
         const int r = (int)(e - i * k);
         a.bperm[e] = a.B[(int64_t)__ldg(&a.perm[i]) * a.brs + (int64_t)r * a.bcs];
@@ -987,23 +1355,39 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32, 1) solve_kernel(SolveArgs a)
             tile_compute<KT>(a, dir, use_perm, tr, lane, 0, 1, stage, acc, nw);
             tile_store<KT>(a, dir, tr, lane, acc);
           }
-          __syncthreads();      // CTA-scope ordering: the level's results are visible to the whole slot
+          cta_sync();           // CTA-scope ordering: the level's results are visible to the whole slot
         }
       }
-    } else if (ph.pad == 8) {
-      level_phase<KT, 8>(a, ph, p, use_perm, lane, warp, stage, part, have_next, s_next);
-    } else if (ph.pad == 16) {
-      level_phase<KT, 16>(a, ph, p, use_perm, lane, warp, stage, part, have_next, s_next);
+    } else if constexpr (pipe) {
+      const int th_ = (int)(ph.pad & 0xff);
+      if (a.trace && blockIdx.x == 0 && threadIdx.x == 0) a.trace[16 * p + 9] = clock64();
+      if (th_ == 8) level_phase_pipe<KT, 8>(a, ph, p, use_perm, lane, warp, stage, part, cs, sm);
+      else if (th_ == 16) level_phase_pipe<KT, 16>(a, ph, p, use_perm, lane, warp, stage, part, cs, sm);
+      else level_phase_pipe<KT, SOLVE_TILE>(a, ph, p, use_perm, lane, warp, stage, part, cs, sm);
     } else {
-      level_phase<KT, SOLVE_TILE>(a, ph, p, use_perm, lane, warp, stage, part, have_next, s_next);
+      // the tiles read their panel entries themselves: column-major panels, or (SOLVE_TILED) the tile-major ones
+      const int th_ = (int)(ph.pad & 0xff);
+      if (ph.pad & SOLVE_TILED) {
+        if (th_ == 8) level_phase<KT, 8, true>(a, ph, p, use_perm, lane, warp, stage, part, have_next, s_next);
+        else if (th_ == 16) level_phase<KT, 16, true>(a, ph, p, use_perm, lane, warp, stage, part, have_next, s_next);
+        else level_phase<KT, SOLVE_TILE, true>(a, ph, p, use_perm, lane, warp, stage, part, have_next, s_next);
+      } else {
+        if (th_ == 8) level_phase<KT, 8, false>(a, ph, p, use_perm, lane, warp, stage, part, have_next, s_next);
+        else if (th_ == 16) level_phase<KT, 16, false>(a, ph, p, use_perm, lane, warp, stage, part, have_next, s_next);
+        else level_phase<KT, SOLVE_TILE, false>(a, ph, p, use_perm, lane, warp, stage, part, have_next, s_next);
+      }
     }
-    // ---- hand the prefetched first tile record of the next phase to the whole warp
-    have_next = nxt_have;
-    if (nxt_have && lane < 5) s_next[warp][lane] = nxt;
-    __syncwarp();
+    if constexpr (!pipe) {
+      // ---- hand the prefetched first tile record of the next phase to the whole warp
+      have_next = nxt_have;
+      if (nxt_have && lane < 5) s_next[warp][lane] = nxt;
+      __syncwarp();
+    }
     if (bar_after) {
       target += gridDim.x;
-      grid_barrier(a.barrier, target);
+      cta_sync();
+      grid_barrier_arrive_wait(a.barrier, target);
+      cta_sync();
     }
     if (a.times && blockIdx.x == 0 && threadIdx.x == 0) {
       unsigned long long t;
@@ -1036,6 +1420,8 @@ struct KernelCfg {
   bool ready = false;
   int grid = 0;
   size_t smem = 0;      // cooperative level kernel: staging + partial sums
+  size_t smem_pipe = 0; // ... + panel rings, mbarriers, slice FIFOs and record slots of the panel pipeline
+  int lring_w = 0;      // panel ring bytes per warp in the level kernel
   size_t smem_sub = 0;  // subtree kernel: staging + panel ring + mbarriers + front records
   int ring_w = 0;       // panel ring bytes per warp
   int rec_cap = 0;      // front records staged in shared memory
@@ -1049,9 +1435,22 @@ int configure(int slot) {
   if (c.ready) return 0;
   const size_t stage_b = (size_t)SOLVE_WARPS * 32 * KT * 8;
   c.smem = 2 * stage_b;
-  EIGD_CUDA(cudaFuncSetAttribute(solve_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
+  {
+    // panel pipeline of the level kernel: what is left of the 227 KB per CTA after the staging / partial-sum arrays,
+    // the kernel's static shared memory (phase records, first-tile records) and the pipeline's own bookkeeping
+    cudaFuncAttributes fa;
+    EIGD_CUDA(cudaFuncGetAttributes(&fa, solve_kernel<KT, true>));
+    const size_t misc = pipe_smem_misc();
+    const size_t budget = 227 * 1024 - fa.sharedSizeBytes - 1024;
+    size_t ring = budget > c.smem + misc ? (budget - c.smem - misc) / SOLVE_WARPS : 0;
+    ring = std::min<size_t>(ring, 16384) / 256 * 256;
+    c.lring_w = ring >= 2048 ? (int)ring : 0;
+    c.smem_pipe = c.lring_w ? c.smem + (size_t)SOLVE_WARPS * c.lring_w + misc : c.smem;
+  }
+  EIGD_CUDA(cudaFuncSetAttribute(solve_kernel<KT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem_pipe));
+  EIGD_CUDA(cudaFuncSetAttribute(solve_kernel<KT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
   int occ = 0;
-  EIGD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, solve_kernel<KT>, SOLVE_WARPS * 32, c.smem));
+  EIGD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, solve_kernel<KT, true>, PIPE_THREADS, c.smem_pipe));
   if (occ < 1) { eigd_set_error("solve: kernel does not fit on an SM"); return 5; }
   // subtree kernel: staging [NW][KT][32] | panel ring | mbarriers + copy queue | front records; 227 KB per CTA on sm_100a
   constexpr int NW = SubCfg<KT>::NW;
@@ -1081,6 +1480,7 @@ int launch_solve(int slot, eigd_factor* f, SolveArgs& a) {
   a.deps = f->h->solve.deps;
   a.dep_ovf = f->h->solve.dep_ovf;
   a.ring_w = c.ring_w;
+  a.lring_w = 0;
   a.rec_cap = c.rec_cap;
   // subtree phases in front mode run as their own launches in front of / behind the cooperative level kernel
   const bool sub_first = np >= 1 && hp[0].ws == 0 && hp[0].pad == 0;
@@ -1098,8 +1498,20 @@ int launch_solve(int slot, eigd_factor* f, SolveArgs& a) {
     a.epoch = ++f->epoch;            // one epoch per cooperative launch: the completion counters never reset
     int nbar = 0;
     for (int p = a.p_begin; p + 1 < a.p_end; ++p) nbar += barrier_between(hp[p], hp[p + 1], p) ? 1 : 0;
+    // tile-major panels (SOLVE_TILED in the level phases' records) <=> the level kernel runs its panel pipeline
+    bool tiled = false;
+    for (int p = a.p_begin; p < a.p_end; ++p) tiled = tiled || (hp[p].ws > 0 && (hp[p].pad & SOLVE_TILED));
+    // the producer / consumer form runs 17 warps per CTA at 96 registers: right for the one- and two-column solves of
+    // the eigensolver (the tiles keep no panel entries in registers; measured 228 -> 218 us and 296 -> 285 us at C2), too
+    // few for wider ones (k = 4: 306 -> 330 us), which keep the 16-warp form and read the tile-major panels themselves
+    // (EIGD_SOLVE_PIPE_KMAX: developer override)
+    static int pipe_kmax = -1;
+    if (pipe_kmax < 0) { const char* e = getenv("EIGD_SOLVE_PIPE_KMAX"); pipe_kmax = e ? atoi(e) : 2; }
+    tiled = tiled && c.lring_w > 0 && KT <= pipe_kmax;
+    a.lring_w = tiled ? c.lring_w : 0;
     void* params[] = {(void*)&a};
-    EIGD_CUDA(cudaLaunchCooperativeKernel((void*)solve_kernel<KT>, dim3(c.grid), dim3(SOLVE_WARPS * 32), params, c.smem,
+    EIGD_CUDA(cudaLaunchCooperativeKernel(tiled ? (void*)solve_kernel<KT, true> : (void*)solve_kernel<KT, false>, dim3(c.grid),
+                                          dim3(tiled ? PIPE_THREADS : SOLVE_WARPS * 32), params, tiled ? c.smem_pipe : c.smem,
                                           g_eigd_stream));
     ++g_eigd_launches;
     f->bar_base += (unsigned long long)nbar * (unsigned long long)c.grid;
@@ -1132,6 +1544,8 @@ int build_solve_plan_dev(eigd_symbolic* S, SymDevHolder* h) {
   rc |= upload_vec(h, P.ovf_row, &d.ovf_row);
   rc |= upload_vec(h, P.ovf, &d.ovf);
   rc |= upload_vec(h, P.sub_ptr, &d.sub_ptr);
+  rc |= upload_vec(h, P.th_fwd, &h->d.th_f);     // storage form of every front's solve panels (panel_build_kernel)
+  rc |= upload_vec(h, P.th_bwd, &h->d.th_b);
   d.nphases = (int)P.phases.size();
   d.host_phases = P.phases;
   return rc;
@@ -1176,7 +1590,7 @@ extern "C" int eigd_solve_timing_end(int64_t* calls_by_k, double* ms_by_k) {
 static unsigned long long* g_phase_times = nullptr;
 static long long* g_trace = nullptr;
 extern "C" int eigd_solve_set_phase_times(void* d_buf) { g_phase_times = (unsigned long long*)d_buf; return 0; }
-// developer profiling: device buffer of 8 * nphases i64 (see SolveArgs::trace)
+// developer profiling: device buffer of 16 * nphases i64 (see SolveArgs::trace)
 extern "C" int eigd_solve_set_trace(void* d_buf) { g_trace = (long long*)d_buf; return 0; }
 extern "C" int eigd_solve_num_phases(const eigd_factor* f) { return f->h->solve.nphases; }
 

@@ -189,6 +189,18 @@ void build_solve_plan_host(const eigd_symbolic* S, int target_warps, int nslots,
       while (to > 8 && count_tiles(dir, l, to / 2) <= ncta) to /= 2;
       height[(size_t)dir * S->nlevels + l] = to;
     }
+  // tile-major panels + the asynchronous shared-memory panel pipeline of the level kernel (EIGD_SOLVE_PIPE=0: column-major
+  // panels read straight from global memory, the round-1 / early round-2 form, kept for comparison runs)
+  bool tiled = true;
+  if (const char* e = getenv("EIGD_SOLVE_PIPE")) tiled = atoi(e) != 0;
+  P.th_fwd.assign(ns, 0);
+  P.th_bwd.assign(ns, 0);
+  if (tiled)
+    for (int k = 0; k < ns; ++k)
+      if (S->sn_level[k] > cut) {
+        P.th_fwd[k] = height[(size_t)0 * S->nlevels + S->sn_level[k]];
+        P.th_bwd[k] = height[(size_t)1 * S->nlevels + S->sn_level[k]];
+      }
   auto level_phase = [&](int dir, int l) {
     int redmax = 1;
     const int to = height[(size_t)dir * S->nlevels + l];
@@ -198,7 +210,7 @@ void build_solve_plan_host(const eigd_symbolic* S, int target_warps, int nslots,
     }
     const int64_t nt = count_tiles(dir, l, to);
     const int ws = pick_ws((int)nt, redmax, target_warps);
-    PhaseRec ph{dir, ws, 0, l, (int64_t)P.tiles.size(), to};
+    PhaseRec ph{dir, ws, 0, l, (int64_t)P.tiles.size(), to | (tiled ? SOLVE_TILED : 0)};
     // tiles of front k in direction d, in the tile height of ITS level's phase (completion-counter targets)
     auto ntile = [&](int k, int d) {
       const int tk = S->sn_level[k] > cut ? height[(size_t)d * S->nlevels + S->sn_level[k]] : SOLVE_TILE;
@@ -273,6 +285,8 @@ extern "C" int64_t eigd_solve_plan_get(const eigd_symbolic* s, int target_warps,
     case 5: return copy_out64(P.sub_ptr, out, cap);
     case 6: return copy_out64(P.sub_slot, out, cap);
     case 8: return copy_out64(P.slab, out, cap);
+    case 11: return copy_out64(P.th_fwd, out, cap);
+    case 12: return copy_out64(P.th_bwd, out, cap);
     case 9: {
       std::vector<int64_t> flat;
       flat.reserve(P.deps.size() * 8);

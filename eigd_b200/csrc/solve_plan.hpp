@@ -31,6 +31,20 @@ constexpr int64_t LINK_HAS_CHILDREN = (int64_t)1 << 57;
 #endif
 EIGD_HD inline int64_t solve_panel_doubles(int f, int nc) { return ((int64_t)f * nc + 1) & ~(int64_t)1; }
 
+// Reduction entries per warp when ws warps split a reduction of length len: an EVEN count, so that every warp's slice
+// of a tile-major panel (below) starts on a 16-byte boundary -- the unit of a bulk copy into shared memory.
+EIGD_HD inline int solve_slice_len(int len, int ws) { return (((len + ws - 1) / ws) + 1) & ~1; }
+
+// TILE-MAJOR solve panels of the fronts ABOVE the cut (level phases; PhaseRec::pad carries SOLVE_TILED).  With tile
+// height TH (outputs per warp tile: 32, 16 or 8, chosen per level and direction) the f x nc panel S of a front is
+// stored tile by tile: row tile t (rows t TH ... , th = min(TH, f - t TH) of them) occupies th * nc doubles from
+// offset t TH nc, element (row r, column c) at c * th + (r - t TH).  S^T (nc x f) likewise by column tiles: tile t
+// (tw = min(TH, nc - t TH) pivot columns) from offset t TH f, element (column c, front row i) at i * tw + (c - t TH).
+// The part of a tile that one warp multiplies -- a contiguous range of the reduction dimension -- is then ONE
+// contiguous run of doubles, which the level kernel brings into shared memory with one bulk copy, ahead of time.
+// Fronts below the cut keep plain column-major panels (the subtree kernels copy whole fronts).
+constexpr int64_t SOLVE_TILED = 0x100;   // flag in PhaseRec::pad next to the tile height (low byte)
+
 // One warp tile: 32 consecutive outputs of one front.  Everything the warp needs about the front
 // travels in this one 48-byte record; the forward sweep needs no further index look-up before it
 // can read its operands (permuted right-hand side and the two child slabs are addressed by the
@@ -94,6 +108,7 @@ struct SolvePlanHost {
   int nslots = 0;
   std::vector<int> sub_ptr;       // two tables (forward, backward) of nslots * (cut_level + 2) tile indices
   std::vector<int> sub_slot;      // owning slot of every supernode below the cut (-1 above it)
+  std::vector<int> th_fwd, th_bwd;  // per supernode: tile height of its tile-major S / S^T panel, 0 = column-major
 };
 
 // target_warps: resident warps the level phases are balanced for; nslots: CTA slots of the subtree

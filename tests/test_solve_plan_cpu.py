@@ -100,9 +100,9 @@ def emulate(plan, S, sym_arr, dinv, b, shuffle=None):
     height = {}                        # tile index -> tile height of its level phase (PhaseRec.pad)
     for d, ws, ntiles, level, tile_off, _to in plan["phases"]:
         if ws > 0:
-            assert int(_to) in (8, 16, 32)
+            assert int(_to) & 0xff in (8, 16, 32)          # low byte: tile height; 0x100: tile-major panel storage
             for te in range(tile_off, tile_off + ntiles):
-                height[int(te)] = int(_to)
+                height[int(te)] = int(_to) & 0xff
 
     def run_level_tile(te, d):
         selfc, deps = tile_deps(plan, te)
@@ -197,7 +197,7 @@ def test_plan_emulation_matches_scipy(nx, ny, dof, use_coords):
         # the level keeps the full height; thinner tiles only add to the count)
         assert len([1 for k in done if k[0] == 0]) >= ntiles_f
         assert len([1 for k in done if k[0] == 1]) >= ntiles_b
-        if int(plan["phases"][:, 5][plan["phases"][:, 1] > 0].min(initial=32)) == 32:
+        if int((plan["phases"][:, 5][plan["phases"][:, 1] > 0] & 0xff).min(initial=32)) == 32:
             assert len([1 for k in done if k[0] == 0]) == ntiles_f and len([1 for k in done if k[0] == 1]) == ntiles_b
         cutl = int(plan["meta"][0])
         seen_cut.add(cutl)

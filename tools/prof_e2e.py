@@ -40,9 +40,13 @@ def step():
 
 for _ in range(3): step()
 D.COPY_STATS.clear(); STAMPS.clear()
+D.Timeline.reset(); D.Timeline.enabled = True; D.solve_timing_begin()
 t0 = time.perf_counter()
 for _ in range(3): step()
 print("e2e step %.1f ms" % ((time.perf_counter() - t0) / 3 * 1e3))
+D.Timeline.enabled = False
+print("  GPU time by entry point (CUDA events, ms/step):", {k: round(v["ms"] / 3, 2) for k, v in D.Timeline.summary().items()})
+print("  solves by k (calls/step, ms/call):", {k: (v[0] / 3, round(v[1] / max(v[0], 1), 4)) for k, v in D.solve_timing_end().items()})
 for k, (c, sec, nb) in D.COPY_STATS.items():
     print("  %-52s %5.1f calls/step %7.2f ms/step %7.1f MB/step" % (k, c / 3, sec / 3 * 1e3, nb / 3 / 1e6))
 print("  host wall clock per call: " + ", ".join("%s %.2f ms" % (k, v / 3 * 1e3) for k, v in STAMPS.items()))

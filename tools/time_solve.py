@@ -57,16 +57,20 @@ for k in ((1,) if os.environ.get("EIGD_SOLVE_DBG") else (1, 2, 4, 10)):
     lib.eigd_solve_set_phase_times(None)
     print("k=%d phase us:" % k, " ".join("%.1f" % (v / 1e3) for v in acc), " total %.1f" % (acc.sum() / 1e3))
 # per-tile trace of CTA 0 / warp 0 (clock64 deltas in ns at the SM clock reported by nvidia-smi)
-tr = torch.zeros(8 * nph, dtype=torch.int64, device="cuda")
+tr = torch.zeros(16 * nph, dtype=torch.int64, device="cuda")
 B = torch.randn(n, dtype=torch.float64, device="cuda")
 X = torch.empty_like(B)
 lib.eigd_solve_set_trace(ctypes.c_void_p(tr.data_ptr()))
 for it in range(3):
     f.lu.solve(B, out=X); torch.cuda.synchronize()
 lib.eigd_solve_set_trace(None)
-t = tr.cpu().numpy().reshape(nph, 8)
-print("trace (cycles): phase: wait | product | reduce | store | signal")
+t = tr.cpu().numpy().reshape(nph, 16)
+print("trace (cycles): phase: wait (of which panel copy) | product | reduce | store | signal | bookkeeping || start-to-start")
+prev = 0
 for p in range(nph):
     if t[p, 0]:
-        print("  %2d: %6d %6d %6d %6d %6d   total %6d" % (p, t[p, 1] - t[p, 0], t[p, 2] - t[p, 1], t[p, 3] - t[p, 2], t[p, 4] - t[p, 3],
-                                                     t[p, 5] - t[p, 4], t[p, 5] - t[p, 0]))
+        print("  %2d: %6d (%5d) %6d %6d %6d %6d %6d   total %6d || %6d" % (
+            p, t[p, 1] - t[p, 0], max(t[p, 6] - t[p, 0], 0) if t[p, 6] else 0, t[p, 2] - t[p, 1], t[p, 3] - t[p, 2], t[p, 4] - t[p, 3],
+            t[p, 5] - t[p, 4], max(t[p, 7] - t[p, 5], 0) if t[p, 7] else 0, t[p, 5] - t[p, 0], t[p, 0] - prev if prev else 0),
+            "| loop top -> dispatch %5d -> tile start %5d" % (t[p, 9] - t[p, 8], t[p, 0] - t[p, 9]) if t[p, 8] and t[p, 9] else "")
+        prev = t[p, 0]
