@@ -269,6 +269,45 @@ def shell_case(nx=16, ny=14, ncx=4, ncy=3, N=6, m=30, omega0=10.0, seed=5):
     return out
 
 
+def transient_heat_funcs(tfinal):
+    """The heat loads of the example's own transient run (reference examples/thermal.py:1665-1690)."""
+    beta = 50 / tfinal
+    H = lambda t: 0.5 + 0.5 * np.tanh(beta * t)                                   # noqa: E731
+    interval = lambda t, t0, t1: (H(t - t0) + H(t1 - t) - 1.0)                    # noqa: E731
+    interval0 = lambda t, t0, t1: interval(t, t0, t1) - interval(0, t0, t1)      # noqa: E731
+    f = {"center": lambda t: 10 * interval0(t, 0.1 * tfinal, 1.5 * tfinal)}
+    for k in range(4):
+        f["corner%d" % k] = lambda t: -2.5 * interval0(t, 0.1 * tfinal, 1.5 * tfinal)
+    return {"test": f}
+
+
+def transient_flow(th, nx=32, N=8, m=40, nsteps=100, tfinal=25.0, ks_rho=10.0, seed=2):
+    """Transient thermal KS objective and its gradient (reference examples/thermal.py: ThermalOpt :997-1321 over
+    ThermalTopologyAnalysis built by make_opt_model :1512).  Shared by the golden generator (th = the example loaded
+    against the reference) and by tests/test_dropin_examples_gpu.py (th = the same file loaded against the alias)."""
+    element_sets = {"center": [], "corner0": [], "corner1": [], "corner2": [], "corner3": []}
+    topo = th.make_opt_model(nx=nx, rfact=4.0, N=N, m=m, p=3, epsilon=1e-5, solver_type="IRAM", adjoint_method="sibk",
+                             adjoint_options=dict(SIBK), element_sets=element_sets, eig_atol=1e-5, rtol=1e-12,
+                             deriv_type="tensor")
+    np.random.seed(seed)
+    topo.x[:] = np.random.uniform(0.3, 1.0, topo.x.shape)
+    opt = th.ThermalOpt(topo, transient_heat_funcs(tfinal), nsteps=nsteps, tfinal=tfinal)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        opt.initialize()
+        ks = opt.eval_ks_functions(ks_rho)
+        opt.initialize_adjoint()
+        opt.add_ks_derivative(ks_rho, {"test": 1.0})
+        opt.finalize_adjoint()
+    return {"nx": nx, "N": N, "m": m, "nsteps": nsteps, "tfinal": tfinal, "ks_rho": ks_rho, "seed": seed, "x": topo.x.copy(),
+            "lam": np.asarray(topo.lam).copy(), "ks": float(np.real(ks["test"])), "xi": np.asarray(opt.xi["test"]).copy(),
+            "lamb": np.asarray(topo.lamb).copy(), "xb": np.asarray(topo.xb).copy()}
+
+
+def transient_case():
+    return transient_flow(rl.load_example("thermal"))
+
+
 if __name__ == "__main__":
     if not rl.reference_available():
         raise SystemExit("reference tree not available; fixtures cannot be regenerated here")
@@ -279,6 +318,7 @@ if __name__ == "__main__":
         "buckling_basiclanczos": buckling_case,
         "shell_iram": shell_case,
         "objectives": objectives_case,
+        "thermal_transient": transient_case,
     }
     only = set(sys.argv[1:])
     for name, fn in cases.items():

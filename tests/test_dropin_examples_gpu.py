@@ -148,3 +148,21 @@ def test_buckling_example_unmodified(rl):
         assert rel(topo.psir * s, g["psi_" + method]) < 1e-8, method
         assert rel(topo.rhob, g["rhob_" + method]) < 1e-8, method
         assert rel(topo.xb, g["xb_" + method]) < 1e-8, method
+
+
+def test_transient_thermal_ks_example_unmodified(rl):
+    """examples/thermal.py ThermalOpt (:997-1321: modal transient heat equations, KS aggregate of the mean temperatures
+    and its adjoint) over ThermalTopologyAnalysis built by make_opt_model (:1512), both unmodified, on the alias -- the
+    flow of make_golden.transient_flow, shared with the golden generator."""
+    g = dict(np.load(os.path.join(ROOT, "tests", "golden", "thermal_transient.npz")))
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_golden
+    th = rl.load_example("thermal", against="alias")
+    assert "eigd_b200" in th.IRAM.__module__
+    out = make_golden.transient_flow(th, nx=int(g["nx"]), N=int(g["N"]), m=int(g["m"]), nsteps=int(g["nsteps"]),
+                                     tfinal=float(g["tfinal"]), ks_rho=float(g["ks_rho"]), seed=int(g["seed"]))
+    assert np.array_equal(out["x"], g["x"])
+    assert rel(out["lam"], g["lam"]) < 1e-10
+    assert abs(out["ks"] - float(g["ks"])) < 1e-8 * abs(float(g["ks"]))
+    assert rel(out["lamb"], g["lamb"]) < 1e-8
+    assert rel(out["xb"], g["xb"]) < 1e-8
