@@ -14,13 +14,14 @@
 // in the forward sweep, its parent in the backward sweep -- and the panel entries of its first chunk are already
 // in flight while it waits (TileDep in solve_plan.hpp).
 //
-// Mapping.  512-thread CTAs, one (or two) per SM, cooperative launch.  A warp tile is 32 consecutive
-// outputs of one front (lane = output), the reduction dimension is streamed in chunks of 32 whose
-// input vectors are staged in shared memory ([k][32] per warp) while the panel entries are read
-// straight from HBM, coalesced across the lanes (column-major panels: consecutive lanes = consecutive
-// addresses).  On the upper levels, where a level has few tiles, ws warps share a tile and split its
-// reduction dimension; partial sums meet in shared memory.  Update vectors are gathered (pull lists
-// built on the host), never scattered: no atomics, bitwise reproducible sums.
+// Mapping.  512-thread CTAs (16 tile warps), one per SM, cooperative launch.  A warp tile is 32 (16, 8 on the upper
+// levels) consecutive outputs of one front (lane = output), the reduction dimension is streamed in chunks of 32 whose
+// input vectors are staged in shared memory ([k][32] per warp).  Panels of the fronts above the cut are stored
+// tile-major (solve_plan.hpp): for one- and two-column solves a 17th PRODUCER warp streams every warp's panel slices
+// into shared-memory rings ahead of time (cp.async.bulk + mbarriers, section "ASYNCHRONOUS PANEL PIPELINE" below);
+// wider solves read the entries straight from HBM, coalesced across the lanes.  On the upper levels, where a level
+// has few tiles, ws warps share a tile and split its reduction dimension; partial sums meet in shared memory.  Update
+// vectors are gathered (pull lists built on the host), never scattered: no atomics, bitwise reproducible sums.
 //
 // Algorithmic bytes per call: 2*(nnz(L)*8 + idx) + n*8 + 4*n*k*8.
 #include "factor_internal.cuh"
