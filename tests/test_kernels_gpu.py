@@ -289,3 +289,49 @@ def test_mgs_sweep(D, n, k, j):
     H3 = D.zeros(j, k)
     D.mgs_sweep(wt, [D.to_device(W) for W in Ws], [H3[t] for t in range(j)])
     assert rel(wt.cpu().numpy(), ref) < 1e-13
+
+
+SOLVE_VARIANT_SCRIPT = r"""
+import sys, numpy as np
+sys.path.insert(0, %(root)r); sys.path.insert(0, %(tests)r); sys.path.insert(0, %(oracle)r)
+from test_kernels_gpu import grid_matrix
+from eigd_b200 import device as D
+D.init("cuda:0")
+for nx, ny, dof in ((250, 200, 1), (60, 45, 2), (9, 7, 1)):
+    rng = np.random.default_rng(nx + ny + dof)
+    A, X = grid_matrix(nx, ny, dof, rng)
+    n = A.shape[0]
+    sym = D.Symbolic(A.indptr, A.indices, n, coords=X, dof_per_node=dof)
+    Ad = D.CsrDevice.from_scipy(A)
+    fac = D.Factor(sym, max_rhs=32).numeric(Ad.data, sym.assembly_map_device(Ad.indptr, Ad.indices))
+    for k in (1, 2, 4, 10, 16):
+        B = rng.normal(size=(n, k))
+        Bd = D.to_device(B)
+        X1 = fac.solve(Bd).cpu().numpy()
+        r = np.abs(A @ X1 - B).max() / np.abs(B).max()
+        assert r < 1e-11, (nx, k, r)
+        assert np.array_equal(X1, fac.solve(Bd).cpu().numpy()), "solve is not bitwise reproducible"
+print("variants ok")
+"""
+
+
+@pytest.mark.parametrize("env", [
+    {"EIGD_SOLVE_PIPE": "0"},            # column-major panels, every tile loads its panel entries itself (the round-1 form)
+    {"EIGD_SOLVE_PIPE_KMAX": "0"},       # tile-major panels, no producer warp for any k
+    {"EIGD_SOLVE_PIPE_KMAX": "16"},      # producer / consumer kernel for every k (96 registers: slower for wide tiles, must be correct)
+    {"EIGD_SOLVE_DBG": "8"},             # the pipeline copies nothing: every slice takes the larger-than-the-ring path
+    {"EIGD_SOLVE_THIN": "0"},            # 32-output tiles on every level
+    {"EIGD_LANCZOS_LOCAL": "0"},         # (no effect on the solve; keeps the switch alive)
+])
+def test_solve_kernel_variants(env):
+    """The developer switches of the triangular solve select other kernels / panel layouts than the default; each must
+    solve the same systems to the same residual (they are what the A/B timings under profiles/ were measured with)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    e = dict(os.environ)
+    e.update(env)
+    code = SOLVE_VARIANT_SCRIPT % {"root": root, "tests": os.path.join(root, "tests"), "oracle": os.path.join(root, "oracle")}
+    p = subprocess.run([sys.executable, "-c", code], env=e, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0 and "variants ok" in p.stdout, (env, p.stdout[-2000:], p.stderr[-4000:])
