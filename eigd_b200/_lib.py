@@ -51,6 +51,7 @@ SIGNATURES = {
     "eigd_solve_timing_end": (c_int, [c_ptr, c_ptr]),
     "eigd_solve_set_phase_times": (c_int, [c_ptr]),
     "eigd_solve_set_trace": (c_int, [c_ptr]),
+    "eigd_solve_set_skew": (c_int, [c_ptr]),
     "eigd_solve_num_phases": (c_int, [c_ptr]),
     "eigd_lanczos_extend": (c_int, [c_ptr, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_int,
                                     c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_ptr]),

@@ -77,6 +77,9 @@ struct SolveArgs {
   int lring_w;                    // bytes of shared-memory panel ring per warp in the level kernel (0: no panel pipeline)
   int rec_cap;                    // tile records of a slot that fit in shared memory
   unsigned long long* times;      // developer profiling: %globaltimer of CTA 0 after every phase (NULL: off)
+  unsigned long long* skew;       // developer profiling: %globaltimer of EVERY CTA's warp 0 in its first tile of every level
+                                  // phase of the pipelined kernel, 4 slots per (phase, CTA): tile start, slot there,
+                                  // dependencies complete, signalled (NULL: off)
   long long* trace;               // developer profiling: clock64 of CTA 0 / warp 0 inside its first tile of every level
                                   // phase, 16 slots per phase: 0 start, 1 waited, 2 product done, 3 reduced, 4 stored,
                                   // 5 signalled, 6 slot (record + panel slice) there, 7 end of tile, 8 top of the phase loop,
@@ -1196,8 +1199,12 @@ __device__ __forceinline__ void level_phase_pipe(const SolveArgs& a, const Phase
     sto.di = 0.0;
     sto.dst = 0;
     const bool tr_on = a.trace && blockIdx.x == 0 && ct == (int)blockIdx.x && threadIdx.x == 0;
+    const bool sk_on = a.skew && threadIdx.x == 0 && ct == (int)blockIdx.x && have;
+    unsigned long long* sk = a.skew + ((size_t)p * gridDim.x + blockIdx.x) * 4;
+    auto gtime = [] { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; };
     if (have) {
       if (tr_on) a.trace[16 * p + 0] = clock64();
+      if (sk_on) sk[0] = gtime();
       mbar_wait(&sm.full[cs.slot], cs.par);                 // record written, panel slice landed
       const int4* r = sm.rec + cs.slot * PIPE_REC_INT4;
       tr = unpack_tile(r[0], r[1], r[2]);
@@ -1206,10 +1213,12 @@ __device__ __forceinline__ void level_phase_pipe(const SolveArgs& a, const Phase
       dw.td.d1 = d1.x; dw.td.n1 = d1.y; dw.td.ovf = d1.z; dw.td.pad = 0;
       dw.pending = dw.td.ndep > 0;
       if (KT <= 2 && slice == 0) sto = tile_store_request<TH>(a, dir, tr, lane);
-      if (a.trace) {                // trace build of the chain: wait first so that the segments separate
+      if (a.trace || a.skew) {      // trace builds of the chain: wait first so that the segments separate
         if (tr_on) a.trace[16 * p + 6] = clock64();
+        if (sk_on) sk[1] = gtime();
         dw(lane);
         if (tr_on) a.trace[16 * p + 1] = clock64();
+        if (sk_on) sk[2] = gtime();
       }
       // the slice: in the warp's ring, or (larger than the ring, rare) where it lies in global memory -- same code,
       // generic loads
@@ -1251,6 +1260,7 @@ __device__ __forceinline__ void level_phase_pipe(const SolveArgs& a, const Phase
       if (tr_on) a.trace[16 * p + 4] = clock64();
       signal_done(a.cnt + dw.td.self);
       if (tr_on) a.trace[16 * p + 5] = clock64();
+      if (sk_on) sk[3] = gtime();
     }
     if (ws > 1) consumer_sync();
     if (tr_on) a.trace[16 * p + 7] = clock64();
@@ -1590,9 +1600,12 @@ extern "C" int eigd_solve_timing_end(int64_t* calls_by_k, double* ms_by_k) {
 // developer profiling hook: device buffer of (nphases + 1) u64 receiving per-phase timestamps of the next solves
 static unsigned long long* g_phase_times = nullptr;
 static long long* g_trace = nullptr;
+static unsigned long long* g_skew = nullptr;
 extern "C" int eigd_solve_set_phase_times(void* d_buf) { g_phase_times = (unsigned long long*)d_buf; return 0; }
 // developer profiling: device buffer of 16 * nphases i64 (see SolveArgs::trace)
 extern "C" int eigd_solve_set_trace(void* d_buf) { g_trace = (long long*)d_buf; return 0; }
+// developer profiling: device buffer of 4 * nphases * (number of SMs) u64 (see SolveArgs::skew)
+extern "C" int eigd_solve_set_skew(void* d_buf) { g_skew = (unsigned long long*)d_buf; return 0; }
 extern "C" int eigd_solve_num_phases(const eigd_factor* f) { return f->h->solve.nphases; }
 
 extern "C" int eigd_factor_solve(eigd_factor* f, const double* B, int64_t brs, int64_t bcs, double* X, int64_t xrs,
@@ -1634,6 +1647,7 @@ extern "C" int eigd_factor_solve(eigd_factor* f, const double* B, int64_t brs, i
     a.k = kc;
     a.times = g_phase_times;
     a.trace = g_trace;
+    a.skew = g_skew;
     {
       static int dbg = -1;
       if (dbg < 0) { const char* e = getenv("EIGD_SOLVE_DBG"); dbg = e ? atoi(e) : 0; }

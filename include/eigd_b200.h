@@ -139,6 +139,9 @@ int eigd_solve_set_phase_times(void* d_buf);
 /* developer profiling: d_buf (device, 8 x nphases int64) receives clock64 stamps of CTA 0 / warp 0 inside its first
  * tile of every level phase (start, dependencies met, product done, partials reduced, stored, signalled) */
 int eigd_solve_set_trace(void* d_buf);
+/* developer profiling: d_buf = 4 * nphases * (number of SMs) u64, %globaltimer of every CTA's first tile of every level
+ * phase of the pipelined level kernel (start, slot there, dependencies complete, signalled); NULL switches it off */
+int eigd_solve_set_skew(void* d_buf);
 int eigd_solve_num_phases(const eigd_factor* f);
 int64_t eigd_factor_bytes(const eigd_factor* f);
 

@@ -74,3 +74,26 @@ for p in range(nph):
             t[p, 5] - t[p, 4], max(t[p, 7] - t[p, 5], 0) if t[p, 7] else 0, t[p, 5] - t[p, 0], t[p, 0] - prev if prev else 0),
             "| loop top -> dispatch %5d -> tile start %5d" % (t[p, 9] - t[p, 8], t[p, 0] - t[p, 9]) if t[p, 8] and t[p, 9] else "")
         prev = t[p, 0]
+# skew of the dependency chain across CTAs (pipelined level kernel, k = 1): %globaltimer of every CTA's first tile per phase
+nsm = torch.cuda.get_device_properties(0).multi_processor_count
+sk = torch.zeros(nph * nsm * 4, dtype=torch.int64, device="cuda")
+lib.eigd_solve_set_skew(ctypes.c_void_p(sk.data_ptr()))
+for it in range(3):
+    sk.zero_()
+    f.lu.solve(B, out=X); torch.cuda.synchronize()
+lib.eigd_solve_set_skew(None)
+s_ = sk.cpu().numpy().reshape(nph, nsm, 4).astype(np.float64)
+print("skew (ns, all CTAs with a tile in the phase): CTAs | dependencies complete: spread (max - min) | signalled - deps complete: min / median / max |"
+      " last signal -> first deps complete of the next phase")
+prev_last = None
+for p in range(nph):
+    m = s_[p, :, 3] > 0
+    if not m.any():
+        prev_last = None
+        continue
+    dep, sig = s_[p, m, 2], s_[p, m, 3]
+    work = sig - dep
+    hop = (dep.min() - prev_last) if prev_last else float("nan")
+    print("  %2d: %3d | %6.0f | %6.0f %6.0f %6.0f | %6.0f   phase %6.0f" % (p, m.sum(), dep.max() - dep.min(), work.min(), np.median(work),
+                                                                  work.max(), hop, sig.max() - dep.min()))
+    prev_last = sig.max()
